@@ -1,0 +1,135 @@
+// common.cuh — shared host/device pieces of libpbrt_b200 (sm_100a only).
+//
+// The whole library is compiled with -fmad=false: the reference is Rust, which never contracts
+// a*b+c, so no kernel may either unless it asks for it explicitly (__fmaf_rn / fma.rn.f32x2 in
+// the PBRT_SPLAT_FMA path).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/pbrt_b200.h"
+
+namespace pb {
+
+struct Bounds { int x0, y0, x1, y1; };
+
+__host__ __device__ inline int bw(const Bounds &b) { return b.x1 - b.x0; }
+__host__ __device__ inline int bh(const Bounds &b) { return b.y1 - b.y0; }
+
+// ---- colour matrices: src/core/spectrum.rs:129-145, evaluated left to right ----
+__device__ __forceinline__ void rgb_to_xyz(float r, float g, float b, float &x, float &y, float &z) {
+    x = 0.412453f * r + 0.357580f * g + 0.180423f * b;
+    y = 0.212671f * r + 0.715160f * g + 0.072169f * b;
+    z = 0.019334f * r + 0.119193f * g + 0.950227f * b;
+}
+__device__ __forceinline__ void xyz_to_rgb(float x, float y, float z, float &r, float &g, float &b) {
+    r = 3.240479f * x - 1.537150f * y - 0.498535f * z;
+    g = -0.969256f * x + 1.875991f * y + 0.041556f * z;
+    b = 0.055648f * x - 0.204043f * y + 1.057311f * z;
+}
+// RGBSpectrum::y() of pbrt-v3; weights = row 2 of rgb_to_xyz (spectrum.rs:142)
+__device__ __forceinline__ float luminance(float r, float g, float b) {
+    return 0.212671f * r + 0.715160f * g + 0.072169f * b;
+}
+
+// ---- PCG32: src/core/rng.rs:19-93 ----
+struct Pcg32 {
+    uint64_t state, inc;
+    __host__ __device__ uint32_t next_u32() {
+        uint64_t old = state;
+        state = old * 0x5851f42d4c957f2dULL + inc;
+        uint32_t xorshifted = (uint32_t)(((old >> 18) ^ old) >> 27);
+        uint32_t rot = (uint32_t)(old >> 59);
+        return (xorshifted >> rot) | (xorshifted << ((~rot + 1u) & 31));
+    }
+    __host__ __device__ void set_sequence(uint64_t seq) {
+        state = 0;
+        inc = (seq << 1) | 1;
+        next_u32();
+        state += 0x853c49e6748fea9bULL;
+        next_u32();
+    }
+    __device__ float next_float() {
+        float v = __uint2float_rn(next_u32()) * 2.3283064365386963e-10f;
+        const float one_minus_eps = 1.f - 1.1920929e-07f;
+        return one_minus_eps < v ? one_minus_eps : v;
+    }
+};
+
+// ---- streaming loads / stores (data touched once: keep it out of L1) ----
+__device__ __forceinline__ float4 ldg_stream(const float4 *p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float2 ldg_stream(const float2 *p) {
+    float2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void stg_stream(float4 *p, float4 v) {
+    asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
+                 "f"(v.w)
+                 : "memory");
+}
+
+}  // namespace pb
+
+// ---- the film object behind the opaque handle ----
+struct PbrtFilm {
+    int xres, yres;
+    float crop[4];
+    float radius[2], inv_radius[2];
+    float diagonal_m, scale, max_lum;
+    pb::Bounds cropped;  // cropped_pixel_bounds of the whole film
+    pb::Bounds owned;    // rows stored by this handle (== cropped unless sharded)
+    int64_t npix;
+    float table[256];
+    float4 *d_xyzw;   // {xyz, filter_weight_sum} per owned pixel
+    float *d_splat;   // splat_xyz, 3 floats per owned pixel
+    float *d_table;   // 256 floats
+    int *d_err;       // sticky async error word
+    int device;
+    // grow-only staging for host-pointer calls
+    void *d_stage[2];
+    size_t stage_bytes[2];
+    float4 *d_scratch_tile;  // add_samples (arbitrary order) scratch
+    size_t scratch_tile_px;
+};
+
+namespace pb {
+
+struct Ctx {
+    bool ready;
+    int device;
+    int sm_count;
+    cudaStream_t own_stream;
+    cudaStream_t stream;
+    uint64_t launches;
+};
+Ctx &ctx();
+int fail(int code, const char *fmt, ...);
+int cuda_fail(cudaError_t e, const char *what);
+int ensure_ready();
+int stage_in(PbrtFilm *f, int slot, const void *host, size_t bytes, void **dev_out);
+
+#define PB_CUDA(expr)                                          \
+    do {                                                       \
+        cudaError_t _e = (expr);                               \
+        if (_e != cudaSuccess) return pb::cuda_fail(_e, #expr); \
+    } while (0)
+
+#define PB_LAUNCH_CHECK(name)                                     \
+    do {                                                          \
+        pb::ctx().launches++;                                     \
+        cudaError_t _e = cudaGetLastError();                      \
+        if (_e != cudaSuccess) return pb::cuda_fail(_e, name);    \
+    } while (0)
+
+// kernels implemented in splat.cu
+int launch_splat_tile(PbrtFilm *f, const Bounds &sb, const Bounds &tb, int spp, const float2 *xy, const float4 *rgbw,
+                      int mode);
+
+}  // namespace pb

@@ -1,0 +1,476 @@
+// splat.cu — [T2, extension] FilmTile::add_sample for a pixel-major sample stream, fused with
+// merge_film_tile.  The reference declares the fields this needs (src/core/film.rs:428-436) but
+// has no add_sample; the algorithm is pbrt-v3 7.9.2, restated on the CPU in
+// oracle/pbrt_oracle.c:orc_ext_tile_add_sample.
+//
+// Three implementations of the same contract:
+//
+//   window gather (hot path, radius with h = floor(r + .5) in 1..4, equal on both axes)
+//     A sample at nominal pixel n only ever touches pixels n-h .. n+h, so an output pixel can
+//     GATHER: walk the samples of its (2h+1)^2 neighbouring pixels in stream order and add the
+//     ones whose footprint covers it.  No atomics, fixed order => bit-reproducible, and with
+//     mul-then-add identical to the CPU restatement.
+//     A thread owns one pixel COLUMN of a CTA-wide strip and marches down the rows holding a
+//     2h+1-row window of RGBW accumulators in registers.  Per sample row the CTA first runs a
+//     pre-pass, one thread per sample (coalesced float2 + float4 loads): luminance clamp,
+//     L*sample_weight, and the table ROW offset (ify*16) of each of the 2h+1 window rows packed
+//     one per byte (0xFF = row outside the footprint).  Records go to shared memory with a padded
+//     pixel pitch so that lanes reading sample s of consecutive pixels hit distinct banks.
+//     The gather then costs, per (sample, column): one LDS.128 + one LDS.32/64, the ifx index
+//     (5 FP ops), and per covered row PRMT + LEA + LDS(table) + 4 packed f32x2 ops.
+//     When the oldest window row can no longer be reached it is converted (rgb_to_xyz) and
+//     added to the film: one float4 read-modify-write per pixel per call.
+//
+//   generic gather (any radius): thread per output pixel, samples read through L1/L2.
+//
+//   scatter with shared-memory atomics (PBRT_SPLAT_ATOMIC): the textbook formulation, kept for
+//     the ncu comparison in profiles/; the order of additions is not deterministic.
+#include <stdio.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace pb {
+
+struct SplatParams {
+    Bounds sb;      // sample bounds (nominal pixels that carry samples)
+    Bounds tb;      // tile pixel bounds = get_film_tile(sb), already clipped to the film
+    Bounds owned;   // film rows/cols stored
+    int spp;
+    float rx, ry, irx, iry;
+    float max_lum;
+    const float2 *xy;
+    const float4 *rgbw;
+    const float *table;  // 256 floats, device
+    float4 *film;
+    int *err;
+    int rows_per_cta;
+};
+
+// ---- pieces shared by all variants -------------------------------------------------------
+
+// min(floor(|v|), 15) as an int, v already multiplied out; |v| < 2^23 or NaN.
+// Adding 2^23 with round-toward-minus-infinity leaves floor(t) in the low mantissa bits.
+__device__ __forceinline__ int table_index(float v) {
+    float t = fminf(fabsf(v), 15.f);
+    return __float_as_int(__fadd_rd(t, 8388608.f)) & 0xF;
+}
+
+__device__ __forceinline__ void clamp_luminance(float4 &L, float max_lum) {
+    float ly = luminance(L.x, L.y, L.z);
+    if (ly > max_lum) {
+        float s = max_lum / ly;
+        L.x *= s; L.y *= s; L.z *= s;
+    }
+}
+
+// film[p] += to_xyz(rgb sum), weight: the body of merge_film_tile (film.rs:318-324)
+__device__ __forceinline__ void flush_pixel(float4 *film, const Bounds &owned, int x, int y, float r, float g, float b,
+                                            float w) {
+    size_t fo = (size_t)(y - owned.y0) * (owned.x1 - owned.x0) + (x - owned.x0);
+    float4 p = film[fo];
+    float X, Y, Z;
+    rgb_to_xyz(r, g, b, X, Y, Z);
+    p.x += X; p.y += Y; p.z += Z; p.w += w;
+    film[fo] = p;
+}
+
+// ---- generic gather ----------------------------------------------------------------------
+
+template <bool FMA>
+__global__ void __launch_bounds__(256) splat_gather_generic_kernel(SplatParams P, int hx, int hy) {
+    __shared__ float s_table[256];
+    s_table[threadIdx.x] = P.table[threadIdx.x];
+    __syncthreads();
+    const int x = P.tb.x0 + blockIdx.x * 32 + (threadIdx.x & 31);
+    const int y = P.tb.y0 + blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= P.tb.x1 || y >= P.tb.y1) return;
+    const int W = P.sb.x1 - P.sb.x0;
+    const float fx = (float)x, fy = (float)y;
+    float ar = 0.f, ag = 0.f, ab = 0.f, aw = 0.f;
+    const int ny0 = max(P.sb.y0, y - hy), ny1 = min(P.sb.y1 - 1, y + hy);
+    const int nx0 = max(P.sb.x0, x - hx), nx1 = min(P.sb.x1 - 1, x + hx);
+    for (int ny = ny0; ny <= ny1; ++ny)
+        for (int nx = nx0; nx <= nx1; ++nx) {
+            const size_t base = ((size_t)(ny - P.sb.y0) * W + (nx - P.sb.x0)) * (size_t)P.spp;
+            for (int s = 0; s < P.spp; ++s) {
+                const float2 p = P.xy[base + s];
+                if (!(p.x >= (float)nx && p.x < (float)(nx + 1) && p.y >= (float)ny && p.y < (float)(ny + 1)))
+                    atomicOr(P.err, PBRT_E_NOT_PIXEL_MAJOR);
+                const float dx = p.x - 0.5f, dy = p.y - 0.5f;
+                // x in [ceil(dx - r), floor(dx + r)]  <=>  dx - r <= x <= dx + r for integer x
+                if (!(fx >= dx - P.rx && fx <= dx + P.rx && fy >= dy - P.ry && fy <= dy + P.ry)) continue;
+                float4 L = P.rgbw[base + s];
+                clamp_luminance(L, P.max_lum);
+                const int ix = table_index((fx - dx) * P.irx * 16.f);
+                const int iy = table_index((fy - dy) * P.iry * 16.f);
+                const float w = s_table[iy * 16 + ix];
+                if (FMA) {
+                    ar = __fmaf_rn(L.x * L.w, w, ar); ag = __fmaf_rn(L.y * L.w, w, ag); ab = __fmaf_rn(L.z * L.w, w, ab);
+                } else {
+                    ar += L.x * L.w * w; ag += L.y * L.w * w; ab += L.z * L.w * w;
+                }
+                aw += w;
+            }
+        }
+    flush_pixel(P.film, P.owned, x, y, ar, ag, ab, aw);
+}
+
+// ---- window gather -----------------------------------------------------------------------
+
+typedef unsigned long long u64;
+
+__device__ __forceinline__ u64 pack2(float lo, float hi) {
+    u64 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(u64 v, float &lo, float &hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ u64 add2(u64 a, u64 b) {
+    u64 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
+    u64 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+
+template <int H>
+struct WinCfg {
+    static constexpr int ROWS = 2 * H + 1;
+    static constexpr int NW = (ROWS + 3) / 4;  // 32-bit words of packed row bytes per sample
+};
+
+// shared-memory layout for one sample row of a CTA strip
+template <int H, int TW>
+struct WinSmem {
+    static constexpr int NPX = TW + 2 * H;
+    __host__ __device__ static int pitch_a(int spp) { return spp + 1; }                      // float4 units per pixel
+    __host__ __device__ static int pitch_b(int spp) { return (spp * WinCfg<H>::NW) | 1; }    // u32 units per pixel
+    __host__ __device__ static size_t bytes(int spp) {
+        return 2048 + (size_t)NPX * pitch_a(spp) * 16 + (size_t)NPX * pitch_b(spp) * 4;
+    }
+};
+
+template <int H, int TW, bool FMA>
+__global__ void __launch_bounds__(TW) splat_window_kernel(SplatParams P) {
+    constexpr int ROWS = WinCfg<H>::ROWS;
+    constexpr int NW = WinCfg<H>::NW;
+    constexpr int NPX = WinSmem<H, TW>::NPX;
+    extern __shared__ __align__(16) unsigned char smem[];
+    // [0,2048): table with every weight stored twice, so one LDS.64 yields the (w, w) operand
+    float2 *s_tab = reinterpret_cast<float2 *>(smem);
+    float4 *s_a = reinterpret_cast<float4 *>(smem + 2048);
+    const int pitch_a = WinSmem<H, TW>::pitch_a(P.spp);
+    const int pitch_b = WinSmem<H, TW>::pitch_b(P.spp);
+    unsigned *s_b = reinterpret_cast<unsigned *>(smem + 2048 + (size_t)NPX * pitch_a * 16);
+
+    const int tid = threadIdx.x;
+    for (int i = tid; i < 256; i += TW) {
+        float w = P.table[i];
+        s_tab[i] = make_float2(w, w);
+    }
+
+    const int cx0 = P.tb.x0 + blockIdx.x * TW;             // first output column of the strip
+    const int cy0 = P.tb.y0 + blockIdx.y * P.rows_per_cta; // first output row
+    const int cy1 = min(cy0 + P.rows_per_cta, P.tb.y1);
+    const int x = cx0 + tid;
+    const bool col_ok = x < P.tb.x1;
+    const float fx = (float)x;
+    const int spp = P.spp;
+    const int W = P.sb.x1 - P.sb.x0;
+
+    // staged nominal pixels of a row: [sx0, sx1), local index = nx - (cx0 - H)
+    const int sx0 = max(cx0 - H, P.sb.x0), sx1 = min(cx0 + TW + H, P.sb.x1);
+    const int nstaged = max(sx1 - sx0, 0) * spp;
+    const unsigned tab_addr = (unsigned)__cvta_generic_to_shared(s_tab);
+
+    u64 acc_rg[ROWS], acc_bw[ROWS];
+#pragma unroll
+    for (int j = 0; j < ROWS; ++j) acc_rg[j] = acc_bw[j] = 0ull;
+
+    for (int ny = cy0 - H; ny < cy1 + H; ++ny) {
+        const bool row_has_samples = ny >= P.sb.y0 && ny < P.sb.y1 && nstaged > 0;
+        if (row_has_samples) {
+            __syncthreads();  // previous row fully consumed (also orders the table fill)
+            // ---------------- pre-pass: one thread per sample of the row ----------------
+            const size_t row_base = ((size_t)(ny - P.sb.y0) * W + (sx0 - P.sb.x0)) * (size_t)spp;
+            const float fny = (float)ny;
+            for (int e = tid; e < nstaged; e += TW) {
+                const float2 p = ldg_stream(&P.xy[row_base + e]);
+                float4 L = ldg_stream(&P.rgbw[row_base + e]);
+                const int pl_rel = e / spp;  // pixel within the staged run
+                const int s = e - pl_rel * spp;
+                const int nx = sx0 + pl_rel;
+                const float fnx = (float)nx;
+                if (!(p.x >= fnx && p.x < fnx + 1.f && p.y >= fny && p.y < fny + 1.f))
+                    atomicOr(P.err, PBRT_E_NOT_PIXEL_MAJOR);
+                clamp_luminance(L, P.max_lum);
+                const float pdx = p.x - 0.5f, pdy = p.y - 0.5f;
+                const float lo = pdy - P.ry, hi = pdy + P.ry;
+                unsigned words[NW];
+#pragma unroll
+                for (int k = 0; k < NW; ++k) words[k] = 0;
+#pragma unroll
+                for (int j = 0; j < ROWS; ++j) {
+                    const float fr = fny + (float)(j - H);
+                    unsigned b = (unsigned)table_index((fr - pdy) * P.iry * 16.f) << 4;
+                    if (j == 0 || j == ROWS - 1) {  // only the outermost rows can fall outside
+                        if (!(fr >= lo && fr <= hi)) b = 0xFFu;
+                    }
+                    words[j >> 2] |= b << (8 * (j & 3));
+                }
+                const int pl = nx - (cx0 - H);
+                s_a[pl * pitch_a + s] = make_float4(L.x * L.w, L.y * L.w, L.z * L.w, pdx);
+#pragma unroll
+                for (int k = 0; k < NW; ++k) s_b[pl * pitch_b + s * NW + k] = words[k];
+            }
+            __syncthreads();
+            // ---------------- gather: this thread's column against the row ----------------
+            if (col_ok) {
+#pragma unroll
+                for (int d = -H; d <= H; ++d) {
+                    const int nx = x + d;
+                    if (nx < P.sb.x0 || nx >= P.sb.x1) continue;
+                    const int pl = nx - (cx0 - H);
+                    const float4 *pa = s_a + pl * pitch_a;
+                    const unsigned *pbw = s_b + pl * pitch_b;
+#pragma unroll 2
+                    for (int s = 0; s < spp; ++s) {
+                        float4 a = pa[s];
+                        unsigned yw[NW];
+#pragma unroll
+                        for (int k = 0; k < NW; ++k) yw[k] = pbw[s * NW + k];
+                        const float pdx = a.w;
+                        // outermost columns: x must lie in [ceil(pdx - r), floor(pdx + r)]
+                        if (d == H) { if (!(fx >= pdx - P.rx)) continue; }
+                        if (d == -H) { if (!(fx <= pdx + P.rx)) continue; }
+                        const float t = fminf(fabsf((fx - pdx) * P.irx * 16.f), 15.f);
+                        // byte address of table column ifx in the duplicated table: ifx * 8
+                        const unsigned xaddr = tab_addr + ((unsigned)(__float_as_int(__fadd_rd(t, 8388608.f)) & 0xF) << 3);
+                        const u64 Lrg = pack2(a.x, a.y);
+                        const u64 Lb1 = pack2(a.z, 1.f);
+#pragma unroll
+                        for (int j = 0; j < ROWS; ++j) {
+                            const unsigned b = __byte_perm(yw[j >> 2], 0, 0x4440 + (j & 3));
+                            if (j == 0 || j == ROWS - 1) { if (b == 0xFFu) continue; }
+                            if (FMA) {
+                                u64 ww;
+                                asm volatile("ld.shared.b64 %0, [%1];" : "=l"(ww) : "r"(xaddr + (b << 3)));
+                                acc_rg[j] = fma2(Lrg, ww, acc_rg[j]);
+                                acc_bw[j] = fma2(Lb1, ww, acc_bw[j]);
+                            } else {
+                                // ptxas fuses mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even with --fmad=false,
+                                // so the products are formed by scalar FMULs and only the adds are packed.
+                                float w;
+                                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(w) : "r"(xaddr + (b << 3)));
+                                acc_rg[j] = add2(acc_rg[j], pack2(a.x * w, a.y * w));
+                                acc_bw[j] = add2(acc_bw[j], pack2(a.z * w, w));
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        // output row ny - H is complete: no later sample row reaches it
+        const int yo = ny - H;
+        if (col_ok && yo >= cy0 && yo < cy1) {
+            float r, g, b, w;
+            unpack2(acc_rg[0], r, g);
+            unpack2(acc_bw[0], b, w);
+            flush_pixel(P.film, P.owned, x, yo, r, g, b, w);
+        }
+#pragma unroll
+        for (int j = 0; j + 1 < ROWS; ++j) { acc_rg[j] = acc_rg[j + 1]; acc_bw[j] = acc_bw[j + 1]; }
+        acc_rg[ROWS - 1] = acc_bw[ROWS - 1] = 0ull;
+    }
+}
+
+// ---- scatter with shared-memory atomics --------------------------------------------------
+
+// CTA = 32x8 nominal pixels; accumulates into a (32+2h)x(8+2h) shared tile with atomics and
+// flushes it with global atomics into a scratch RGBW tile (overlapping halos of neighbouring CTAs).
+constexpr int AT_W = 32, AT_H = 8;
+
+__global__ void __launch_bounds__(256) splat_atomic_kernel(SplatParams P, int hx, int hy, float4 *__restrict__ scratch) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    float *s_table = reinterpret_cast<float *>(smem);
+    float *s_tile = s_table + 256;
+    const int tw = AT_W + 2 * hx, th = AT_H + 2 * hy;
+    for (int i = threadIdx.x; i < 256; i += 256) s_table[i] = P.table[i];
+    for (int i = threadIdx.x; i < tw * th * 4; i += 256) s_tile[i] = 0.f;
+    __syncthreads();
+    const int bx0 = P.sb.x0 + blockIdx.x * AT_W, by0 = P.sb.y0 + blockIdx.y * AT_H;
+    const int nx = bx0 + (threadIdx.x & 31), ny = by0 + (threadIdx.x >> 5);
+    const int W = P.sb.x1 - P.sb.x0;
+    const int ox = bx0 - hx, oy = by0 - hy;  // film coords of smem tile origin
+    if (nx < P.sb.x1 && ny < P.sb.y1) {
+        const size_t base = ((size_t)(ny - P.sb.y0) * W + (nx - P.sb.x0)) * (size_t)P.spp;
+        for (int s = 0; s < P.spp; ++s) {
+            // lanes walk consecutive pixels: a 2-D strided read, spp*8 B apart
+            const float2 p = P.xy[base + s];
+            float4 L = P.rgbw[base + s];
+            if (!(p.x >= (float)nx && p.x < (float)(nx + 1) && p.y >= (float)ny && p.y < (float)(ny + 1)))
+                atomicOr(P.err, PBRT_E_NOT_PIXEL_MAJOR);
+            clamp_luminance(L, P.max_lum);
+            const float dx = p.x - 0.5f, dy = p.y - 0.5f;
+            const int p0x = max(max(__float2int_ru(dx - P.rx), P.tb.x0), ox);
+            const int p0y = max(max(__float2int_ru(dy - P.ry), P.tb.y0), oy);
+            const int p1x = min(min(__float2int_rd(dx + P.rx) + 1, P.tb.x1), ox + tw);
+            const int p1y = min(min(__float2int_rd(dy + P.ry) + 1, P.tb.y1), oy + th);
+            const float cr = L.x * L.w, cg = L.y * L.w, cb = L.z * L.w;
+            for (int y = p0y; y < p1y; ++y) {
+                const int iy = table_index(((float)y - dy) * P.iry * 16.f);
+                for (int x = p0x; x < p1x; ++x) {
+                    const int ix = table_index(((float)x - dx) * P.irx * 16.f);
+                    const float w = s_table[iy * 16 + ix];
+                    float *px = s_tile + ((y - oy) * tw + (x - ox)) * 4;
+                    atomicAdd(px + 0, cr * w);
+                    atomicAdd(px + 1, cg * w);
+                    atomicAdd(px + 2, cb * w);
+                    atomicAdd(px + 3, w);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    const int ttw = P.tb.x1 - P.tb.x0;
+    for (int i = threadIdx.x; i < tw * th; i += 256) {
+        const int x = ox + i % tw, y = oy + i / tw;
+        if (x < P.tb.x0 || x >= P.tb.x1 || y < P.tb.y0 || y >= P.tb.y1) continue;
+        const float *v = s_tile + i * 4;
+        if (v[3] == 0.f && v[0] == 0.f && v[1] == 0.f && v[2] == 0.f) continue;
+        float *o = reinterpret_cast<float *>(&scratch[(size_t)(y - P.tb.y0) * ttw + (x - P.tb.x0)]);
+        atomicAdd(o + 0, v[0]); atomicAdd(o + 1, v[1]); atomicAdd(o + 2, v[2]); atomicAdd(o + 3, v[3]);
+    }
+}
+
+__global__ void __launch_bounds__(256) merge_scratch_kernel(float4 *__restrict__ film, Bounds owned, Bounds tb,
+                                                            const float4 *__restrict__ tile) {
+    const int tw = tb.x1 - tb.x0;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= tw) return;
+    for (int y = blockIdx.y; y < tb.y1 - tb.y0; y += gridDim.y) {
+        float4 t = tile[(size_t)y * tw + x];
+        flush_pixel(film, owned, tb.x0 + x, tb.y0 + y, t.x, t.y, t.z, t.w);
+    }
+}
+
+// ---- launch ------------------------------------------------------------------------------
+
+template <int H, int TW, bool FMA>
+static int launch_window(const SplatParams &P0) {
+    SplatParams P = P0;
+    const size_t smem = WinSmem<H, TW>::bytes(P.spp);
+    static bool attr_set = false;
+    if (!attr_set) {
+        PB_CUDA(cudaFuncSetAttribute(splat_window_kernel<H, TW, FMA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     227 * 1024));
+        attr_set = true;
+    }
+    const int cols = (bw(P.tb) + TW - 1) / TW;
+    const int rows = bh(P.tb);
+    // aim for ~ (resident CTAs per SM) x SMs CTAs, but keep strips tall enough to amortise the halo rows
+    int per_sm = (int)std::max<size_t>(1, std::min<size_t>(2048 / TW, (227 * 1024) / smem));
+    int want = ctx().sm_count * per_sm;
+    int segs = std::max(1, std::min((want + cols - 1) / cols, (rows + 8 * H - 1) / (8 * H)));
+    P.rows_per_cta = (rows + segs - 1) / segs;
+    segs = (rows + P.rows_per_cta - 1) / P.rows_per_cta;
+    dim3 grid(cols, segs);
+    splat_window_kernel<H, TW, FMA><<<grid, TW, smem, ctx().stream>>>(P);
+    PB_LAUNCH_CHECK("splat_window_kernel");
+    return PBRT_OK;
+}
+
+template <int H, bool FMA>
+static int pick_width(const SplatParams &P) {
+    // widest strip whose row of records leaves room for >= 2 CTAs per SM, else whatever fits
+    if (WinSmem<H, 128>::bytes(P.spp) * 2 <= 227 * 1024) return launch_window<H, 128, FMA>(P);
+    if (WinSmem<H, 64>::bytes(P.spp) * 2 <= 227 * 1024) return launch_window<H, 64, FMA>(P);
+    if (WinSmem<H, 32>::bytes(P.spp) <= 227 * 1024) return launch_window<H, 32, FMA>(P);
+    return -1;
+}
+
+template <bool FMA>
+static int pick_window(const SplatParams &P, int h) {
+    switch (h) {
+    case 1: return pick_width<1, FMA>(P);
+    case 2: return pick_width<2, FMA>(P);
+    case 3: return pick_width<3, FMA>(P);
+    case 4: return pick_width<4, FMA>(P);
+    }
+    return -1;
+}
+
+static int g_force_generic = 0;
+
+int launch_splat_tile(PbrtFilm *f, const Bounds &sb, const Bounds &tb, int spp, const float2 *xy, const float4 *rgbw,
+                      int mode) {
+    SplatParams P;
+    P.sb = sb; P.tb = tb; P.owned = f->owned;
+    P.spp = spp;
+    P.rx = f->radius[0]; P.ry = f->radius[1];
+    P.irx = f->inv_radius[0]; P.iry = f->inv_radius[1];
+    P.max_lum = f->max_lum;
+    P.xy = xy; P.rgbw = rgbw;
+    P.table = f->d_table;
+    P.film = f->d_xyzw;
+    P.err = f->d_err;
+    P.rows_per_cta = 0;
+    if (!(P.rx > 0.f) || !(P.ry > 0.f) || P.rx > 1024.f || P.ry > 1024.f)
+        return fail(PBRT_E_UNSUPPORTED, "filter radius (%g, %g) outside (0, 1024]", P.rx, P.ry);
+    // a sample in nominal pixel n reaches pixels n - h .. n + h, h = floor(r + .5)
+    const int hx = (int)floorf(P.rx + 0.5f), hy = (int)floorf(P.ry + 0.5f);
+
+    if (mode == PBRT_SPLAT_ATOMIC) {
+        const size_t px = (size_t)bw(tb) * bh(tb);
+        const size_t smem = 1024 + (size_t)(AT_W + 2 * hx) * (AT_H + 2 * hy) * 16;
+        if (smem > 227 * 1024) return fail(PBRT_E_UNSUPPORTED, "radius too large for the shared-memory tile");
+        if (px > f->scratch_tile_px) {
+            cudaFree(f->d_scratch_tile);
+            f->d_scratch_tile = nullptr;
+            f->scratch_tile_px = 0;
+            PB_CUDA(cudaMalloc(&f->d_scratch_tile, px * sizeof(float4)));
+            f->scratch_tile_px = px;
+        }
+        PB_CUDA(cudaMemsetAsync(f->d_scratch_tile, 0, px * sizeof(float4), ctx().stream));
+        static bool attr_set = false;
+        if (!attr_set) {
+            PB_CUDA(cudaFuncSetAttribute(splat_atomic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            attr_set = true;
+        }
+        dim3 grid((bw(sb) + AT_W - 1) / AT_W, (bh(sb) + AT_H - 1) / AT_H);
+        splat_atomic_kernel<<<grid, 256, smem, ctx().stream>>>(P, hx, hy, f->d_scratch_tile);
+        PB_LAUNCH_CHECK("splat_atomic_kernel");
+        dim3 mgrid((bw(tb) + 255) / 256, std::min(bh(tb), 4096));
+        merge_scratch_kernel<<<mgrid, 256, 0, ctx().stream>>>(f->d_xyzw, f->owned, tb, f->d_scratch_tile);
+        PB_LAUNCH_CHECK("merge_scratch_kernel");
+        return PBRT_OK;
+    }
+
+    const bool fma = mode == PBRT_SPLAT_FMA;
+    if (!g_force_generic && hx == hy && hx >= 1 && hx <= 4) {
+        int rc = fma ? pick_window<true>(P, hx) : pick_window<false>(P, hx);
+        if (rc >= 0) return rc;
+    }
+    dim3 grid((bw(tb) + 31) / 32, (bh(tb) + 7) / 8);
+    if (fma)
+        splat_gather_generic_kernel<true><<<grid, 256, 0, ctx().stream>>>(P, hx, hy);
+    else
+        splat_gather_generic_kernel<false><<<grid, 256, 0, ctx().stream>>>(P, hx, hy);
+    PB_LAUNCH_CHECK("splat_gather_generic_kernel");
+    return PBRT_OK;
+}
+
+}  // namespace pb
+
+// test hook: route add_samples_tile through the generic gather regardless of radius
+extern "C" int pbrt_b200_debug_force_generic_splat(int on) {
+    pb::g_force_generic = on;
+    return PBRT_OK;
+}

@@ -1,0 +1,113 @@
+"""Device selection, stream binding and raw device buffers over the C ABI's [UTIL] entry points."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Any, Tuple
+
+import numpy as np
+
+from . import _lib
+
+
+def init(device: int = 0) -> None:
+    _lib.check(_lib.lib.pbrt_b200_init(int(device)))
+
+
+def set_stream(cuda_stream_ptr: int | None) -> None:
+    """Run subsequent work on a caller-owned cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream)."""
+    _lib.check(_lib.lib.pbrt_b200_set_stream(C.c_void_p(cuda_stream_ptr or 0)))
+
+
+def synchronize() -> None:
+    _lib.check(_lib.lib.pbrt_b200_synchronize())
+
+
+def launch_count() -> int:
+    return int(_lib.lib.pbrt_b200_launch_count())
+
+
+def device_info() -> dict:
+    dev, sm, maj, mnr = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
+    mem = C.c_uint64()
+    _lib.check(_lib.lib.pbrt_b200_device_info(C.byref(dev), C.byref(sm), C.byref(maj), C.byref(mnr), C.byref(mem)))
+    return {"device": dev.value, "sm_count": sm.value, "cc": (maj.value, mnr.value), "hbm_bytes": mem.value}
+
+
+class DeviceBuffer:
+    """A raw device allocation (pbrt_b200_malloc / pbrt_b200_free)."""
+
+    def __init__(self, nbytes: int):
+        p = C.c_void_p()
+        _lib.check(_lib.lib.pbrt_b200_malloc(int(nbytes), C.byref(p)))
+        self.ptr = p.value
+        self.nbytes = int(nbytes)
+
+    @staticmethod
+    def from_numpy(a: np.ndarray) -> "DeviceBuffer":
+        a = np.ascontiguousarray(a)
+        b = DeviceBuffer(a.nbytes)
+        if a.nbytes:
+            _lib.check(_lib.lib.pbrt_b200_memcpy_h2d(C.c_void_p(b.ptr), a.ctypes.data_as(C.c_void_p), a.nbytes))
+        return b
+
+    def to_numpy(self, dtype, shape) -> np.ndarray:
+        out = np.empty(shape, dtype=dtype)
+        assert out.nbytes <= self.nbytes
+        if out.nbytes:
+            _lib.check(_lib.lib.pbrt_b200_memcpy_d2h(out.ctypes.data_as(C.c_void_p), C.c_void_p(self.ptr), out.nbytes))
+        return out
+
+    def zero(self) -> None:
+        _lib.check(_lib.lib.pbrt_b200_memset(C.c_void_p(self.ptr), 0, self.nbytes))
+
+    def free(self) -> None:
+        p, self.ptr = self.ptr, None
+        if p:
+            _lib.lib.pbrt_b200_free(C.c_void_p(p))
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class PinnedBuffer:
+    """Page-locked host memory (pbrt_b200_host_alloc) exposed as a numpy array."""
+
+    def __init__(self, dtype, shape):
+        self.shape = tuple(int(s) for s in np.atleast_1d(shape))
+        self.dtype = np.dtype(dtype)
+        n = int(np.prod(self.shape)) * self.dtype.itemsize
+        p = C.c_void_p()
+        _lib.check(_lib.lib.pbrt_b200_host_alloc(n, C.byref(p)))
+        self.ptr = p.value
+        buf = (C.c_char * n).from_address(self.ptr)
+        self.array = np.frombuffer(buf, dtype=self.dtype).reshape(self.shape)
+
+    def free(self) -> None:
+        p, self.ptr = self.ptr, None
+        self.array = None
+        if p:
+            _lib.lib.pbrt_b200_host_free(C.c_void_p(p))
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def as_pointer(buf: Any, dtype=np.float32) -> Tuple[C.c_void_p, int, Any]:
+    """Return (pointer, is_device, keepalive) for a numpy array, DeviceBuffer, or CUDA torch tensor."""
+    if isinstance(buf, DeviceBuffer):
+        return C.c_void_p(buf.ptr), 1, buf
+    if isinstance(buf, np.ndarray):
+        a = np.ascontiguousarray(buf, dtype=dtype)
+        return a.ctypes.data_as(C.c_void_p), 0, a
+    if hasattr(buf, "data_ptr") and hasattr(buf, "is_cuda"):  # torch.Tensor
+        if not buf.is_contiguous():
+            raise ValueError("tensor must be contiguous")
+        return C.c_void_p(buf.data_ptr()), (1 if buf.is_cuda else 0), buf
+    a = np.ascontiguousarray(np.asarray(buf, dtype=dtype))
+    return a.ctypes.data_as(C.c_void_p), 0, a
