@@ -1,0 +1,431 @@
+#!/usr/bin/env python
+"""bench.py — filtered samples/s into the Film on N B200s (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N ...            # the CPU path on the box's host cores
+
+A step is one pass of the hot path over one batch of synthetic samples: get_film_tile ->
+add_sample for every sample -> merge_film_tile, as ONE kernel launch per GPU.
+
+Workload at N=1: BASELINE.json configs[1] — 1920x1080 film, 16 spp stratified samples (SURVEY.md
+App. C, PCG32, seed 1), Gaussian filter radius 2 (alpha 2).  At N>1 the film is sharded by rows,
+one process per GPU, and the job is weak-scaled: every rank owns a 1920x1080 row block of a
+1920x(1080*N) film, so per-GPU work is fixed.  Samples within h = 2 rows of a shard edge are
+processed by both neighbours (no collective on the data path); the final frame is assembled by
+one NCCL all-gather of the resolved rows, timed separately (assemble_ms).
+
+`value`   : samples/s with the sample streams resident in HBM (timed with CUDA events on the
+            launching stream, barrier + synchronize on both sides, max over ranks).
+`e2e`     : the same through the public API with HOST buffers: pinned host samples are copied to
+            the device every step and the resolved RGB frame is read back.
+`roofline`: algorithmic bytes (24 B/sample + 32 B per film pixel per pass) / kernel duration
+            against the measured HBM copy bandwidth (MEASURED_PEAKS.json).
+`cpu_baseline`: the C restatement of the reference's CPU path (oracle/, "port": the reference is
+            Rust and cannot be built here), one thread, on a bounded band of the same workload.
+
+The reference has no add_sample and only a box filter: the splat path is an
+EXTENSION with no reference parity; its checker is the oracle's restatement of pbrt-v3.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+WORKLOADS = {
+    # name: (width, height, spp per pass, filter name, radius, p0, p1, passes per step)
+    "c2": dict(res=(1920, 1080), spp=16, filter="gaussian", radius=(2.0, 2.0), p0=2.0, p1=0.0,
+               label="1920x1080 film, 16 spp stratified, Gaussian r=2 (BASELINE configs[1])"),
+    "c3": dict(res=(3840, 2160), spp=16, filter="mitchell", radius=(2.0, 2.0), p0=1 / 3, p1=1 / 3,
+               label="3840x2160 film, Mitchell r=2, one 16-spp pass of the 64 spp (BASELINE configs[2])"),
+    "c5": dict(res=(7680, 4320), spp=16, filter="lanczos", radius=(4.0, 4.0), p0=3.0, p1=0.0,
+               label="7680x4320 film, Lanczos-sinc r=4, one 16-spp pass of the 256 spp (BASELINE configs[4])"),
+    "c1": dict(res=(64, 64), spp=4, filter="gaussian", radius=(2.0, 2.0), p0=2.0, p1=0.0,
+               label="64x64 film, 4 spp (BASELINE configs[0])"),
+}
+FILTER_KIND = {"box": 0, "triangle": 1, "gaussian": 2, "mitchell": 3, "lanczos": 4}
+
+
+def measured_peak_gbs():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi style clock / throttle-reason samples during the timed region (via NVML)."""
+
+    def __init__(self, index: int, period: float = 0.05):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:  # pragma: no cover
+            self.err = str(e)
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake_slowdown",
+        }
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop_evt.wait(self.period)
+
+    def finish(self) -> dict:
+        self._stop_evt.set()
+        if self.is_alive():
+            self.join(timeout=2)
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "note": "NVML unavailable"}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+# --------------------------------------------------------------------------------------- CPU arm
+
+class CpuArm:
+    """The oracle's splat pass over a band of the workload: `band_rows` pixel rows of the film."""
+
+    def __init__(self, wl: dict, band_rows: int):
+        import oracle
+        from oracle import OracleFilm
+
+        o = oracle.load()
+        W, H = wl["res"]
+        band_rows = min(band_rows, H)
+        table = oracle.filter_table(o, FILTER_KIND[wl["filter"]], wl["radius"], wl["p0"], wl["p1"])
+        y0 = (H - band_rows) // 2
+        y1 = y0 + band_rows
+        # the band is a Film whose crop window is those rows (src/core/film.rs:92-101 supports this natively)
+        self.film = OracleFilm(o, (W, H), [0.0, y0 / H, 1.0, y1 / H], wl["radius"], table)
+        assert self.film.cropped() == (0, y0, W, y1), self.film.cropped()
+        self.sb = (0, y0, W, y1)
+        self.spp = wl["spp"]
+        self.xy, self.rgbw = oracle.synth_samples(o, self.sb, self.spp, 1)
+        self.n = len(self.xy)
+        self.desc = f"{W}x{band_rows} pixel band of the workload ({self.n} samples per step)"
+
+    def step(self, threads: int) -> float:
+        t0 = time.perf_counter()
+        self.film.add_samples_pass(self.sb, self.spp, self.xy, self.rgbw, threads=threads)
+        return time.perf_counter() - t0
+
+
+def run_reference(args, wl, rank, world):
+    """--impl reference: the reference's CPU implementation of the path on the host cores.
+
+    The reference is Rust and cannot be compiled in this image (no rustc/cargo), so this arm times
+    the oracle port (kind "port") with all host threads on a bounded band of the same workload.
+    Under torchrun only rank 0 works; the other ranks exit.
+    """
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    arm = CpuArm(wl, args.ref_band_rows)
+    for _ in range(args.warmup):
+        arm.step(cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        arm.step(cores)
+    sec = (time.perf_counter() - t0) / args.steps
+    rate = arm.n / sec
+    sample = f"{arm.desc}, {cores} threads (pixel rows split across threads; every pixel keeps its stream order)"
+    out = {
+        "impl": "reference",
+        "metric": "filtered samples/s into Film",
+        "value": rate, "unit": "samples/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl["label"], "filter": wl["filter"], "spp_per_pass": wl["spp"], "sample": sample},
+        "cpu_baseline": {"value": rate, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": rate, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "the reference is Rust (no rustc here) and has no add_sample: this is oracle/pbrt_oracle.c, the C "
+                "restatement of its film path plus pbrt-v3's AddSample, on the host cores",
+    }
+    print(json.dumps(out))
+
+
+# --------------------------------------------------------------------------------------- GPU arm
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--mode", default="exact", choices=["exact", "fma", "atomic"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--cpu-band-rows", type=int, default=256, help="band of the film the 1-thread cpu_baseline runs")
+    ap.add_argument("--ref-band-rows", type=int, default=1080, help="band of the film the --impl reference arm runs")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--extras", action="store_true", help="also time merge / resolve / texture kernels")
+    args = ap.parse_args()
+
+    wl = dict(WORKLOADS[args.workload])
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, wl, rank, world)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import pbrt_b200 as pb
+    from pbrt_b200 import dist as pdist
+    from pbrt_b200 import synth
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: libpbrt_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    pb.init(local_rank)
+    stream = torch.cuda.current_stream()
+    pb.set_stream(stream.cuda_stream)
+
+    # ---- the film and this rank's shard -------------------------------------------------
+    W, H1 = wl["res"]
+    H = H1 * world if args.scaling == "weak" else H1
+    spp = wl["spp"]
+    cls = {"gaussian": pb.GaussianFilter, "mitchell": pb.MitchellFilter, "lanczos": pb.LanczosSincFilter,
+           "triangle": pb.TriangleFilter, "box": pb.BoxFilter}[wl["filter"]]
+    if wl["filter"] == "mitchell":
+        filt = cls(wl["radius"], wl["p0"], wl["p1"])
+    elif wl["filter"] in ("gaussian", "lanczos"):
+        filt = cls(wl["radius"], wl["p0"])
+    else:
+        filt = cls(wl["radius"])
+    film = pb.Film.new([W, H], [[0, 0], [1, 1]], filt, 35.0, "bench.pfm", 1.0, float("inf"), rank=rank, nranks=world)
+    cropped, owned = film.cropped_pixel_bounds, film.owned_pixel_bounds
+    full_sb = cropped  # App. C: samples over the cropped pixel bounds
+    my_sb = pdist.shard_sample_bounds(full_sb, (owned.p_min.y, owned.p_max.y), wl["radius"][1])
+    xy_d, rgbw_d, n_local = synth.samples(my_sb.as4(), spp, seed=1, index_bounds=full_sb.as4())
+    n_unique_total = max(cropped.area(), 0) * spp          # every sample counted once
+    n_owned = max(owned.area(), 0) * spp
+    mode = {"exact": pb.SPLAT_EXACT, "fma": pb.SPLAT_FMA, "atomic": pb.SPLAT_ATOMIC}[args.mode]
+    sb_list = [[my_sb.p_min.x, my_sb.p_min.y], [my_sb.p_max.x, my_sb.p_max.y]]
+
+    def step():
+        film.add_samples_tile(sb_list, spp, xy_d, rgbw_d, mode)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    film.check()
+    barrier()
+
+    # ---- timed region: exactly K steps, device time, max over ranks ----------------------
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = pb.launch_count()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    barrier()
+    ev[0].record(stream)
+    for i in range(args.steps):
+        step()
+        ev[i + 1].record(stream)
+    barrier()
+    clocks = sampler.finish()
+    launches = pb.launch_count() - launches0
+    total_ms = ev[0].elapsed_time(ev[-1])
+    per_step = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
+    film.check()
+    t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms_max = float(t.item())
+    ms_per_step = total_ms_max / args.steps
+    value = n_unique_total / (ms_per_step * 1e-3)
+
+    # ---- roofline of the dominant (only) kernel of the step, this rank --------------------
+    peak, peak_src = measured_peak_gbs()
+    kern_ms = sum(per_step) / len(per_step)  # one launch per step: event-to-event = launch duration
+    alg_bytes = n_local * 24 + max(owned.area(), 0) * 32
+    achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
+    roofline = {
+        "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+        "traffic": None, "peak_source": peak_src, "kernel": "splat_window_kernel" if args.mode != "atomic" else "splat_atomic_kernel",
+        "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kern_ms, "kernel_ms_min": min(per_step),
+        "note": "24 B/sample read + 32 B/film pixel RMW per launch; the kernel is issue-bound, not HBM-bound (DESIGN.md)",
+    }
+
+    # ---- final assembly (once per render, not per step) ----------------------------------
+    barrier()
+    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a0.record(stream)
+    frame = pdist.assemble_film_rgb(film, 1.0)
+    a1.record(stream)
+    barrier()
+    assemble_ms = a0.elapsed_time(a1)
+    assert tuple(frame.shape) == (H, W, 3)
+
+    # ---- end to end through the public API with host buffers ------------------------------
+    e2e = None
+    if not args.no_e2e:
+        hxy = pb.PinnedBuffer(np.float32, (n_local, 2))
+        hrgbw = pb.PinnedBuffer(np.float32, (n_local, 4))
+        hout = pb.PinnedBuffer(np.float32, (max(owned.area(), 0), 3))
+        hxy.array[:] = xy_d.to_numpy(np.float32, (n_local, 2))
+        hrgbw.array[:] = rgbw_d.to_numpy(np.float32, (n_local, 4))
+
+        def e2e_step():
+            film.add_samples_tile(sb_list, spp, hxy.array, hrgbw.array, mode)  # H2D of the step's samples inside
+            film.resolve_rgb(1.0, out=hout.array)                              # D2H of the step's result inside
+
+        for _ in range(2):
+            e2e_step()
+        k = max(3, min(args.steps, 10))
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(k):
+            e2e_step()
+        barrier()
+        dt = torch.tensor([(time.perf_counter() - t0) / k], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e = {"value": n_unique_total / float(dt.item()), "unit": "samples/s",
+               "h2d_bytes_per_step": n_local * 24, "d2h_bytes_per_step": max(owned.area(), 0) * 12,
+               "ms_per_step": float(dt.item()) * 1e3,
+               "api": "Film.add_samples_tile(host xy, host rgbw) + Film.resolve_rgb(host out)"}
+        film.check()
+
+    # ---- secondary kernels (Tier 1: merge / resolve / constant texture) -------------------
+    extras = None
+    if args.extras and rank == 0:
+        extras = time_extras(pb, synth, film, torch, stream, peak)
+
+    # ---- CPU baseline beside it: rank 0, N = 1 only --------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        arm = CpuArm(wl, args.cpu_band_rows)
+        arm.step(1)
+        secs = [arm.step(1) for _ in range(3)]
+        cpu = {"value": arm.n / min(secs), "unit": "samples/s", "cores": 1, "kind": "port",
+               "sample": f"{arm.desc}, best of 3, oracle/pbrt_oracle.c on one thread (the reference is single-threaded); "
+                         f"host has {os.cpu_count()} cores"}
+
+    if rank == 0:
+        out = {
+            "metric": "filtered samples/s into Film", "value": value, "unit": "samples/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl["label"] + (f", weak-scaled to 1920x{H} over {world} row shards" if world > 1 and args.scaling == "weak" else ""),
+                       "film": [W, H], "spp_per_pass": spp, "filter": wl["filter"], "radius": list(wl["radius"]),
+                       "mode": args.mode, "samples_per_step": n_unique_total, "samples_per_rank_incl_halo": n_local,
+                       "cache": "inputs_exceed_l2" if n_local * 24 > 126e6 else "inputs_fit_l2",
+                       "parallelism": f"rows x{world}", "tier": "extension (no reference parity): splat; merge+resolve are Tier 1"},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+            "clocks": clocks, "assemble_ms": assemble_ms,
+            "percent_of_hbm_peak": 100.0 * achieved / peak,
+        }
+        if extras:
+            out["extras"] = extras
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def time_extras(pb, synth, film, torch, stream, peak):
+    """Tier-1 kernels on the same film: merge_film_tile (48 B/tile px), resolve (40 B/px), textures."""
+    import numpy as np
+
+    def timed(fn, reps=10):
+        fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        for _ in range(reps):
+            fn()
+        b.record(stream)
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+
+    out = {}
+    ob = film.owned_pixel_bounds
+    npx = ob.area()
+    # whole-frame tile
+    buf, offsets, total = synth.tiles([npx], seed=1)
+    bounds = np.asarray([ob.as4()], dtype=np.int32)
+    ms = timed(lambda: film.merge_tile_raw(ob, buf))
+    out["merge_one_tile"] = {"tile_px_per_s": npx / (ms * 1e-3), "GB/s": npx * 48 / (ms * 1e-3) / 1e9, "frac": npx * 48 / (ms * 1e-3) / 1e9 / peak, "ms": ms}
+    # 16x16 sample tiles with halos, one launch
+    sb = film.get_sample_bounds().as4()
+    tbs, counts = [], []
+    for y in range(sb[1], sb[3], 16):
+        for x in range(sb[0], sb[2], 16):
+            tb, cnt = film._tile_bounds([[x, y], [min(x + 16, sb[2]), min(y + 16, sb[3])]])
+            tbs.append(tb.as4())
+            counts.append(cnt)
+    if len(tbs) <= 65535:
+        buf2, off2, tot2 = synth.tiles(counts, seed=1)
+        b2 = np.asarray(tbs, dtype=np.int32)
+        ms = timed(lambda: film.merge_tiles_raw(b2, off2, buf2, tot2), reps=5)
+        out["merge_16x16_tiles"] = {"tiles": len(tbs), "tile_px_per_s": tot2 / (ms * 1e-3), "GB/s": tot2 * 48 / (ms * 1e-3) / 1e9,
+                                    "frac": tot2 * 48 / (ms * 1e-3) / 1e9 / peak, "ms": ms, "note": "includes the host-side index build and upload"}
+    rgb = torch.empty((npx, 3), dtype=torch.float32, device="cuda")
+    ms = timed(lambda: film.resolve_rgb(1.0, out=rgb))
+    out["resolve_rgb"] = {"px_per_s": npx / (ms * 1e-3), "GB/s": npx * 40 / (ms * 1e-3) / 1e9, "frac": npx * 40 / (ms * 1e-3) / 1e9 / peak, "ms": ms}
+    rgb8 = torch.empty((npx, 3), dtype=torch.uint8, device="cuda")
+    ms = timed(lambda: film.resolve_rgb8(1.0, out=rgb8))
+    out["resolve_rgb8"] = {"px_per_s": npx / (ms * 1e-3), "GB/s": npx * 31 / (ms * 1e-3) / 1e9, "frac": npx * 31 / (ms * 1e-3) / 1e9 / peak, "ms": ms}
+    n = 100_000_000
+    t1 = torch.empty(n, dtype=torch.float32, device="cuda")
+    ms = timed(lambda: pb.ConstantTexture(10.0).evaluate_batch(n, out=t1))
+    out["texture_constant_f32"] = {"lookups_per_s": n / (ms * 1e-3), "GB/s": n * 4 / (ms * 1e-3) / 1e9, "frac": n * 4 / (ms * 1e-3) / 1e9 / peak, "ms": ms}
+    t3 = torch.empty((n, 3), dtype=torch.float32, device="cuda")
+    ms = timed(lambda: pb.ConstantTexture((1.0, 0.0, 0.0)).evaluate_batch(n, out=t3))
+    out["texture_constant_rgb"] = {"lookups_per_s": n / (ms * 1e-3), "GB/s": n * 12 / (ms * 1e-3) / 1e9, "frac": n * 12 / (ms * 1e-3) / 1e9 / peak, "ms": ms}
+    return out
+
+
+if __name__ == "__main__":
+    main()

@@ -209,6 +209,12 @@ class Film:
         for t in tiles:
             t.pixels = None
 
+    def merge_tile_raw(self, tile_bounds, rgbw) -> None:
+        """One tile from a host or device buffer of (pixels, 4) f32."""
+        tb = Bounds2i.of(tile_bounds) if not isinstance(tile_bounds, Bounds2i) else tile_bounds
+        ptr, is_dev, keep = as_pointer(rgbw)
+        _lib.check(_lib.lib.pbrt_film_merge_tile(self._h, _lib.i32x4(tb.as4()), ptr, is_dev))
+
     def merge_tiles_raw(self, bounds: np.ndarray, offsets: np.ndarray, rgbw, total_pixels: Optional[int] = None) -> None:
         bounds = np.ascontiguousarray(bounds, dtype=np.int32)
         offsets = np.ascontiguousarray(offsets, dtype=np.int64)

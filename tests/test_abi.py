@@ -1,0 +1,132 @@
+"""The C-ABI library loads on a CPU-only box and exports exactly what include/pbrt_b200.h declares."""
+import ctypes as C
+import re
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import oracle
+
+ROOT = Path(__file__).resolve().parent.parent
+HEADER = ROOT / "include" / "pbrt_b200.h"
+
+
+def header_symbols():
+    text = re.sub(r"/\*.*?\*/", "", HEADER.read_text(), flags=re.S)
+    return sorted(set(re.findall(r"\b(pbrt_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_exported_and_bound(pb):
+    from pbrt_b200 import _lib
+
+    syms = header_symbols()
+    assert len(syms) >= 40
+    out = subprocess.run(["nm", "-D", "--defined-only", str(_lib.LIB_PATH)], capture_output=True, text=True, check=True).stdout
+    exported = {line.split()[-1] for line in out.splitlines() if " T " in line}
+    missing = [s for s in syms if s not in exported]
+    assert not missing, f"declared in the header but not exported: {missing}"
+    unbound = [s for s in syms if s not in _lib.PROTOTYPES]
+    assert not unbound, f"declared in the header but not bound in _lib.py: {unbound}"
+    extra = [s for s in _lib.PROTOTYPES if s not in syms]
+    assert not extra, f"bound in _lib.py but not declared in the header: {extra}"
+
+
+def test_library_is_sm100a_only(pb):
+    from pbrt_b200 import _lib
+
+    out = subprocess.run(["cuobjdump", "-lelf", str(_lib.LIB_PATH)], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_(\d+a?)", out))
+    assert archs == {"100a"}, archs
+
+
+def test_exact_splat_kernel_has_no_fused_accumulate(pb):
+    """ptxas fuses f32x2 mul+add even with --fmad=false; the exact kernel must not contain FFMA2."""
+    from pbrt_b200 import _lib
+
+    sass = subprocess.run(["cuobjdump", "-sass", str(_lib.LIB_PATH)], capture_output=True, text=True).stdout
+    blocks = re.split(r"\n\s*Function : ", sass)
+    checked = 0
+    for b in blocks:
+        name = b.split("\n", 1)[0]
+        if "splat_window_kernel" in name and "Lb0E" in name:
+            assert "FFMA2" not in b and "FADD2" in b, name
+            checked += 1
+        if "splat_window_kernel" in name and "Lb1E" in name:
+            assert "FFMA2" in b, name
+    assert checked >= 4
+
+
+def test_no_device_is_a_loud_error(pb):
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(pb.PbrtError) as e:
+        pb.init(0)
+    assert e.value.code == 2 and "no CPU fallback" in str(e.value)
+    with pytest.raises(pb.PbrtError):
+        pb.ConstantTexture(10.0).evaluate_batch(4)
+
+
+def test_version_and_last_error(pb):
+    from pbrt_b200 import _lib
+
+    assert _lib.lib.pbrt_b200_version() >= 100
+    assert isinstance(_lib.last_error(), str)
+
+
+# ---- host-side logic of the library that needs no device: the Filter objects
+
+def test_box_filter_matches_reference_doctest(pb, kats):
+    k = kats["box_filter_xwidth_1"]
+    f = pb.BoxFilter.create_box_filter(k["params"])
+    assert list(f.radius()) == k["radius"] and list(f.inv_radius()) == k["inv_radius"]
+    assert f.evaluate((0.25, 0.1)) == 1.0
+    f2 = pb.make_filter("box", k["params"])
+    assert list(f2.radius()) == k["radius"]
+    d = pb.BoxFilter.create_box_filter()
+    assert d.radius() == (0.5, 0.5)
+    with pytest.raises(ValueError):
+        pb.make_filter("nope")
+
+
+@pytest.mark.parametrize("name", list(oracle.FILTERS))
+def test_filter_tables_match_oracle_bit_exact(pb, orc, name):
+    kind, radius, p0, p1 = oracle.FILTERS[name]
+    want = oracle.filter_table(orc, kind, radius, p0, p1)
+    cls = {"box": pb.BoxFilter, "triangle": pb.TriangleFilter, "gaussian": pb.GaussianFilter,
+           "mitchell": pb.MitchellFilter, "lanczos": pb.LanczosSincFilter}[name]
+    f = cls(radius) if name in ("box", "triangle") else (cls(radius, p0) if name != "mitchell" else cls(radius, p0, p1))
+    got = pb.filter_table(f)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+    # the generic path of Film::new (256 evaluate calls through the trait) gives the same table
+    class Wrapped(pb.Filter):
+        def evaluate(self, p):
+            return f.evaluate(p)
+
+        def radius(self):
+            return f.radius()
+
+        def inv_radius(self):
+            return f.inv_radius()
+
+    assert np.array_equal(pb.filter_table(Wrapped()).view(np.uint32), want.view(np.uint32))
+
+
+def test_user_defined_filter_table(pb):
+    class Tent(pb.Filter):
+        def evaluate(self, p):
+            return max(0.0, 1.0 - abs(p[0])) * max(0.0, 1.0 - abs(p[1]))
+
+        def radius(self):
+            return (1.0, 1.0)
+
+        def inv_radius(self):
+            return (1.0, 1.0)
+
+    t = pb.filter_table(Tent()).reshape(16, 16)
+    assert t[0, 0] == np.float32((1 - 0.5 / 16) ** 2) or abs(t[0, 0] - (1 - 0.5 / 16) ** 2) < 1e-7
+    assert np.allclose(t, t.T)

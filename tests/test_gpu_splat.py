@@ -1,0 +1,266 @@
+"""EXTENSION parity (no reference parity exists: the reference has no add_sample): the CUDA
+splat kernels against the CPU restatement of pbrt-v3 FilmTile::AddSample, on identical samples.
+
+PBRT_SPLAT_EXACT must be bit-identical to the oracle (same order, mul then add); PBRT_SPLAT_FMA
+and PBRT_SPLAT_ATOMIC must agree within 1e-5 relative error (BASELINE.json north_star)."""
+import numpy as np
+import pytest
+
+import oracle
+from oracle import OracleFilm
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 1e-5  # north_star: per-pixel RGB and weight sums within 1e-5 relative error
+
+
+def u32(a):
+    return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+
+
+def make_filter(pb, name, radius=None):
+    kind, rad, p0, p1 = oracle.FILTERS[name]
+    rad = radius or rad
+    cls = {"box": pb.BoxFilter, "triangle": pb.TriangleFilter, "gaussian": pb.GaussianFilter,
+           "mitchell": pb.MitchellFilter, "lanczos": pb.LanczosSincFilter}[name]
+    if name in ("box", "triangle"):
+        return cls(rad), kind, rad, p0, p1
+    if name == "mitchell":
+        return cls(rad, p0, p1), kind, rad, p0, p1
+    return cls(rad, p0), kind, rad, p0, p1
+
+
+def run_pair(pb, orc, name, res, crop, sb, spp, mode, radius=None, max_lum=float("inf"), jitter=None, seed=1):
+    filt, kind, rad, p0, p1 = make_filter(pb, name, radius)
+    table = oracle.filter_table(orc, kind, rad, p0, p1)
+    film = pb.Film.new(res, [[crop[0], crop[1]], [crop[2], crop[3]]], filt, 35.0, "x.pfm", 1.0, max_lum)
+    of = OracleFilm(orc, res, crop, rad, table, max_lum=max_lum)
+    xy, rgbw = oracle.synth_samples(orc, sb, spp, seed)
+    if jitter is not None:
+        xy, rgbw = jitter(xy, rgbw)
+    film.add_samples_tile([[sb[0], sb[1]], [sb[2], sb[3]]], spp, xy, rgbw, mode)
+    film.check()
+    of.add_samples_pass(sb, spp, xy, rgbw, threads=4)
+    return film, of
+
+
+def rel_err(got, want):
+    """max over pixels of |got - want| / max(|want|, small) per channel group."""
+    denom = np.maximum(np.abs(want), 1e-3)
+    return float((np.abs(got - want) / denom).max())
+
+
+# ------------------------------------------------------------------ config 1 of BASELINE.json
+
+@pytest.mark.parametrize("name", list(oracle.FILTERS))
+def test_c1_64x64_4spp_each_filter_exact(gpu, orc, name):
+    """BASELINE.json configs[0]: each filter kernel on a 64x64 film, 4 spp."""
+    film, of = run_pair(gpu, orc, name, (64, 64), [0, 0, 1, 1], (0, 0, 64, 64), 4, gpu.SPLAT_EXACT)
+    assert np.array_equal(u32(film.read_pixels()), u32(of.pixels()))
+    assert np.array_equal(u32(film.resolve_rgb(1.0)), u32(of.write_image_rgb(1.0)))
+
+
+@pytest.mark.parametrize("name", list(oracle.FILTERS))
+def test_c1_generic_gather_exact(gpu, orc, name):
+    from pbrt_b200 import _lib
+
+    _lib.lib.pbrt_b200_debug_force_generic_splat(1)
+    try:
+        film, of = run_pair(gpu, orc, name, (64, 64), [0, 0, 1, 1], (0, 0, 64, 64), 4, gpu.SPLAT_EXACT)
+    finally:
+        _lib.lib.pbrt_b200_debug_force_generic_splat(0)
+    assert np.array_equal(u32(film.read_pixels()), u32(of.pixels()))
+
+
+@pytest.mark.parametrize("name", list(oracle.FILTERS))
+@pytest.mark.parametrize("mode", ["fma", "atomic"])
+def test_c1_tolerance_modes(gpu, orc, name, mode):
+    m = gpu.SPLAT_FMA if mode == "fma" else gpu.SPLAT_ATOMIC
+    film, of = run_pair(gpu, orc, name, (64, 64), [0, 0, 1, 1], (0, 0, 64, 64), 4, m)
+    got, want = film.read_pixels(), of.pixels()
+    assert rel_err(got[:, :4], want[:, :4]) <= REL_TOL
+    if mode == "fma":  # the weight sum involves no multiply: identical
+        assert np.array_equal(u32(got[:, 3]), u32(want[:, 3]))
+
+
+# ------------------------------------------------------------------ shapes, clipping, ragged edges
+
+CASES = [
+    # name, res, crop, sample bounds, spp
+    ("gaussian", (301, 77), [0, 0, 1, 1], "film", 16),          # sample bounds reach outside the film
+    ("gaussian", (301, 77), [0.2, 0.1, 0.9, 0.8], "film", 4),   # cropped film
+    ("mitchell", (130, 140), [0, 0, 1, 1], (5, 7, 120, 133), 9),  # tile strictly inside, spp = 3x3
+    ("mitchell", (257, 40), [0, 0, 1, 1], (-2, -2, 259, 42), 1),  # 1 spp, strip width not a multiple of the CTA
+    ("lanczos", (90, 70), [0, 0, 1, 1], "film", 4),             # h = 4
+    ("triangle", (64, 33), [0, 0, 1, 1], (10, 3, 11, 30), 5),   # one pixel column of samples, spp not a square
+    ("box", (50, 50), [0, 0, 1, 1], (0, 0, 50, 50), 7),         # h = 1, footprint 1x1 or 2x2
+    ("gaussian", (40, 300), [0, 0, 1, 1], "film", 2),           # tall: many row segments
+    ("gaussian", (64, 64), [0, 0, 1, 1], (70, 70, 80, 80), 4),  # tile misses the film entirely
+    ("gaussian", (64, 64), [0, 0, 1, 1], (62, 62, 80, 80), 4),  # tile touches one corner
+]
+
+
+@pytest.mark.parametrize("name,res,crop,sb,spp", CASES)
+def test_clipping_and_ragged_shapes_exact(gpu, orc, name, res, crop, sb, spp):
+    if sb == "film":
+        _, kind, rad, p0, p1 = make_filter(gpu, name)
+        sb = OracleFilm(orc, res, crop, rad, np.ones(256, np.float32)).sample_bounds()
+    film, of = run_pair(gpu, orc, name, res, crop, sb, spp, gpu.SPLAT_EXACT)
+    assert np.array_equal(u32(film.read_pixels()), u32(of.pixels()))
+
+
+@pytest.mark.parametrize("radius", [(1.0, 1.0), (1.5, 1.5), (2.5, 2.5), (3.0, 3.0), (3.4, 3.4), (4.4, 4.4)])
+def test_radii_covering_every_window_size(gpu, orc, radius):
+    """h = floor(r + .5) = 1, 2, 3, 3, 3, 4 — including radii where r + .5 is an integer."""
+    film, of = run_pair(gpu, orc, "gaussian", (80, 50), [0, 0, 1, 1], (-4, -4, 84, 54), 4, gpu.SPLAT_EXACT, radius=radius)
+    assert np.array_equal(u32(film.read_pixels()), u32(of.pixels()))
+
+
+@pytest.mark.parametrize("radius", [(8.0, 8.0), (2.0, 3.0), (0.3, 0.3), (5.0, 5.0)])
+def test_radii_served_by_the_generic_gather(gpu, orc, radius):
+    film, of = run_pair(gpu, orc, "triangle", (48, 40), [0, 0, 1, 1], (0, 0, 48, 40), 4, gpu.SPLAT_EXACT, radius=radius)
+    assert np.array_equal(u32(film.read_pixels()), u32(of.pixels()))
+
+
+def test_samples_on_exact_pixel_and_half_pixel_positions(gpu, orc):
+    """Positions where ceil/floor of (p - .5 -+ r) and the table bins sit exactly on their boundaries."""
+    def snap(xy, rgbw):
+        xy = xy.copy()
+        base = np.floor(xy)
+        frac = np.tile(np.array([[0.0, 0.0], [0.5, 0.5], [0.0, 0.5], [0.25, 0.75], [0.5, 0.0], [0.125, 0.375],
+                                 [0.75, 0.25], [0.9999999, 0.5], [0.5, 0.9999999]], dtype=np.float32), (len(xy) // 9 + 1, 1))[: len(xy)]
+        return (base + frac).astype(np.float32), rgbw
+    for name in ("gaussian", "mitchell", "lanczos", "box"):
+        film, of = run_pair(gpu, orc, name, (40, 30), [0, 0, 1, 1], (-4, -4, 44, 34), 9, gpu.SPLAT_EXACT, jitter=snap)
+        assert np.array_equal(u32(film.read_pixels()), u32(of.pixels())), name
+
+
+def test_max_sample_luminance_and_weights(gpu, orc):
+    def bright(xy, rgbw):
+        rgbw = rgbw.copy()
+        rgbw[::3, :3] *= 40.0                       # above the clamp
+        rgbw[:, 3] = 0.25 + (np.arange(len(rgbw)) % 5) * 0.5   # sample weights != 1
+        rgbw[::17, :3] *= -1.0                      # negative radiance stays unclamped
+        return xy, rgbw
+    film, of = run_pair(gpu, orc, "mitchell", (70, 45), [0, 0, 1, 1], (0, 0, 70, 45), 8, gpu.SPLAT_EXACT,
+                        max_lum=2.5, jitter=bright)
+    assert np.array_equal(u32(film.read_pixels()), u32(of.pixels()))
+
+
+def test_accumulates_across_calls_like_successive_tile_merges(gpu, orc):
+    """Several passes into one film == the oracle merging one tile per pass (order of passes kept)."""
+    res, spp = (96, 64), 4
+    filt, kind, rad, p0, p1 = make_filter(gpu, "mitchell")
+    table = oracle.filter_table(orc, kind, rad, p0, p1)
+    film = gpu.Film.new(res, [[0, 0], [1, 1]], filt, 35.0, "x.pfm", 1.0, float("inf"))
+    of = OracleFilm(orc, res, [0, 0, 1, 1], rad, table)
+    for seed, sb in ((1, (0, 0, 96, 64)), (2, (0, 0, 96, 64)), (3, (20, 10, 70, 50))):
+        xy, rgbw = oracle.synth_samples(orc, sb, spp, seed)
+        film.add_samples_tile([[sb[0], sb[1]], [sb[2], sb[3]]], spp, xy, rgbw, gpu.SPLAT_EXACT)
+        of.add_samples_pass(sb, spp, xy, rgbw)
+    film.check()
+    assert np.array_equal(u32(film.read_pixels()), u32(of.pixels()))
+
+
+def test_device_resident_streams_and_synth_generator(gpu, orc):
+    """The device sample generator reproduces the oracle's stream bit for bit; device pointers are used in place."""
+    from pbrt_b200 import synth
+
+    b = (3, 2, 67, 45)
+    xy_d, rgbw_d, n = synth.samples(b, 16, seed=1)
+    xy, rgbw = oracle.synth_samples(orc, b, 16, 1)
+    assert np.array_equal(u32(xy_d.to_numpy(np.float32, (n, 2))), u32(xy))
+    assert np.array_equal(u32(rgbw_d.to_numpy(np.float32, (n, 4))), u32(rgbw))
+    filt, kind, rad, p0, p1 = make_filter(gpu, "gaussian")
+    film = gpu.Film.new((70, 50), [[0, 0], [1, 1]], filt, 35.0, "x.pfm", 1.0, float("inf"))
+    of = OracleFilm(orc, (70, 50), [0, 0, 1, 1], rad, oracle.filter_table(orc, kind, rad, p0, p1))
+    film.add_samples_tile([[3, 2], [67, 45]], 16, xy_d, rgbw_d, gpu.SPLAT_EXACT)
+    film.check()
+    of.add_samples_pass(b, 16, xy, rgbw)
+    assert np.array_equal(u32(film.read_pixels()), u32(of.pixels()))
+    # a shard's generator call reproduces its slice of the whole stream
+    xy_s, rgbw_s, ns = synth.samples((3, 10, 67, 20), 16, seed=1, index_bounds=b)
+    sl = slice((10 - 2) * 64 * 16, (20 - 2) * 64 * 16)
+    assert np.array_equal(u32(xy_s.to_numpy(np.float32, (ns, 2))), u32(xy[sl]))
+
+
+def test_not_pixel_major_is_reported(gpu, orc):
+    filt, kind, rad, p0, p1 = make_filter(gpu, "gaussian")
+    film = gpu.Film.new((32, 32), [[0, 0], [1, 1]], filt, 35.0, "x.pfm", 1.0, float("inf"))
+    xy, rgbw = oracle.synth_samples(orc, (0, 0, 32, 32), 4)
+    xy[100, 0] += 3.0  # leaves its nominal pixel
+    film.add_samples_tile([[0, 0], [32, 32]], 4, xy, rgbw, gpu.SPLAT_EXACT)
+    with pytest.raises(gpu.PbrtError) as e:
+        film.check()
+    assert e.value.code == 4
+    film.check()  # the sticky error is cleared once reported
+
+
+def test_arbitrary_order_add_samples_within_tolerance(gpu, orc):
+    """pbrt_film_add_samples: shuffled samples, global atomics; and FilmTile.add_sample on the host mirror."""
+    res, spp = (48, 36), 4
+    filt, kind, rad, p0, p1 = make_filter(gpu, "gaussian")
+    table = oracle.filter_table(orc, kind, rad, p0, p1)
+    xy, rgbw = oracle.synth_samples(orc, (0, 0, *res), spp)
+    of = OracleFilm(orc, res, [0, 0, 1, 1], rad, table)
+    of.add_samples_pass((0, 0, *res), spp, xy, rgbw)
+    perm = np.random.default_rng(1).permutation(len(xy))
+    film = gpu.Film.new(res, [[0, 0], [1, 1]], filt, 35.0, "x.pfm", 1.0, float("inf"))
+    film.add_samples([[0, 0], list(res)], xy[perm], rgbw[perm])
+    assert rel_err(film.read_pixels()[:, :4], of.pixels()[:, :4]) <= REL_TOL
+    film2 = gpu.Film.new(res, [[0, 0], [1, 1]], filt, 35.0, "x.pfm", 1.0, float("inf"))
+    tile = film2.get_film_tile([[0, 0], list(res)])
+    for p, l in zip(xy[:500], rgbw[:500]):
+        tile.add_sample(p, l[:3], float(l[3]))
+    film2.merge_film_tile(tile)
+    of2 = OracleFilm(orc, res, [0, 0, 1, 1], rad, table)
+    ot = of2.get_film_tile((0, 0, *res))
+    orc.orc_ext_tile_add_samples(ot, 500, oracle.fp(np.ascontiguousarray(xy[:500])), oracle.fp(np.ascontiguousarray(rgbw[:500])))
+    of2.merge(ot)
+    assert rel_err(film2.read_pixels()[:, :4], of2.pixels()[:, :4]) <= REL_TOL
+
+
+# ------------------------------------------------------------------ full-size properties (BASELINE configs[1])
+
+def test_full_size_c2_properties(gpu, orc):
+    """1920x1080, 16 spp, Gaussian r=2 (configs[1]): a cropped band against the oracle bit for bit, and
+    size-independent properties on the whole frame: determinism, linearity in L, weight sums independent of L."""
+    from pbrt_b200 import synth
+
+    res, spp = (1920, 1080), 16
+    filt, kind, rad, p0, p1 = make_filter(gpu, "gaussian")
+    table = oracle.filter_table(orc, kind, rad, p0, p1)
+    b = (0, 0, *res)
+    xy_d, rgbw_d, n = synth.samples(b, spp, seed=1)
+    films = []
+    for _ in range(2):
+        f = gpu.Film.new(res, [[0, 0], [1, 1]], filt, 35.0, "x.pfm", 1.0, float("inf"))
+        f.add_samples_tile([[0, 0], list(res)], spp, xy_d, rgbw_d, gpu.SPLAT_EXACT)
+        f.check()
+        films.append(f.read_pixels())
+    assert np.array_equal(u32(films[0]), u32(films[1]))                       # run-to-run deterministic
+    # oracle on a 1920 x 40 band (rows 500..540): same samples (shard of the stream), bit-exact
+    y0, y1, halo = 500, 540, 3
+    band = (0, y0 - halo, 1920, y1 + halo)
+    xy_b, rgbw_b, nb = synth.samples(band, spp, seed=1, index_bounds=b)
+    of = OracleFilm(orc, res, [0, y0 / 1080, 1, y1 / 1080], rad, table)
+    assert of.cropped() == (0, y0, 1920, y1)
+    of.add_samples_pass(band, spp, xy_b.to_numpy(np.float32, (nb, 2)), rgbw_b.to_numpy(np.float32, (nb, 4)), threads=8)
+    got = films[0].reshape(1080, 1920, 7)[y0:y1].reshape(-1, 7)
+    assert np.array_equal(u32(got), u32(of.pixels()))
+    # weights: every interior pixel received 16 spp x its 5x5 neighbourhood; positive and smooth
+    w = films[0][:, 3].reshape(1080, 1920)
+    assert w.min() > 0 and abs(w[10:-10, 10:-10].mean() / w[540, 960] - 1) < 0.05
+    # linearity: doubling L (a power of two) doubles xyz exactly and leaves the weights untouched
+    rgbw = rgbw_d.to_numpy(np.float32, (n, 4))
+    rgbw[:, :3] *= 2.0
+    rg2 = gpu.DeviceBuffer.from_numpy(rgbw)
+    f2 = gpu.Film.new(res, [[0, 0], [1, 1]], filt, 35.0, "x.pfm", 1.0, float("inf"))
+    f2.add_samples_tile([[0, 0], list(res)], spp, xy_d, rg2, gpu.SPLAT_EXACT)
+    p2 = f2.read_pixels()
+    assert np.array_equal(u32(p2[:, 3]), u32(films[0][:, 3]))
+    assert np.array_equal(u32(p2[:, :3]), u32(films[0][:, :3] * np.float32(2.0)))
+    # fma mode at full size stays inside the tolerance
+    f3 = gpu.Film.new(res, [[0, 0], [1, 1]], filt, 35.0, "x.pfm", 1.0, float("inf"))
+    f3.add_samples_tile([[0, 0], list(res)], spp, xy_d, rgbw_d, gpu.SPLAT_FMA)
+    assert rel_err(f3.read_pixels()[:, :4], films[0][:, :4]) <= REL_TOL
