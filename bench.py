@@ -225,7 +225,8 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     pb.init(local_rank)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()          # one explicit stream for the library, the events and NCCL
+    torch.cuda.set_stream(stream)
     pb.set_stream(stream.cuda_stream)
 
     # ---- the film and this rank's shard -------------------------------------------------

@@ -54,7 +54,8 @@ int pbrt_b200_version(void);
 const char *pbrt_b200_last_error(void);
 /* bind the process to CUDA device `device` and create the library stream */
 int pbrt_b200_init(int device);
-/* run all subsequent work on the caller's stream (a cudaStream_t; NULL = library stream) */
+/* run all subsequent work on the caller's stream (a cudaStream_t; NULL = library stream,
+ * (void*)0x1 = cudaStreamLegacy, the legacy default stream) */
 int pbrt_b200_set_stream(void *cuda_stream);
 int pbrt_b200_synchronize(void);
 int pbrt_b200_device_info(int *device, int *sm_count, int *cc_major, int *cc_minor, uint64_t *hbm_bytes);
@@ -138,7 +139,7 @@ int pbrt_film_merge_tiles(PbrtFilm *film, int32_t ntiles, const int32_t *tile_bo
  * (the method the unused FilmTile fields at film.rs:428-436 exist for; pbrt-v3 7.9.2), as one
  * kernel.  Samples are pixel-major over `sample_bounds` with `spp` per pixel: sample k of
  * pixel (px,py) sits at index ((py-y0)*W + (px-x0))*spp + k and must lie in
- * [px,px+1) x [py,py+1).  xy = 2 floats, rgbw = {L.r, L.g, L.b, sample_weight} per sample.
+ * [px,px+1] x [py,py+1] (closed: px + jitter may round up onto the next pixel boundary).  xy = 2 floats, rgbw = {L.r, L.g, L.b, sample_weight} per sample.
  * Per pixel the samples are accumulated in stream order, then converted and added to the film
  * exactly as merge_film_tile does.
  */

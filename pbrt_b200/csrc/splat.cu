@@ -26,6 +26,7 @@
 //   scatter with shared-memory atomics (PBRT_SPLAT_ATOMIC): the textbook formulation, kept for
 //     the ncu comparison in profiles/; the order of additions is not deterministic.
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <algorithm>
 
@@ -96,7 +97,7 @@ __global__ void __launch_bounds__(256) splat_gather_generic_kernel(SplatParams P
             const size_t base = ((size_t)(ny - P.sb.y0) * W + (nx - P.sb.x0)) * (size_t)P.spp;
             for (int s = 0; s < P.spp; ++s) {
                 const float2 p = P.xy[base + s];
-                if (!(p.x >= (float)nx && p.x < (float)(nx + 1) && p.y >= (float)ny && p.y < (float)(ny + 1)))
+                if (!(p.x >= (float)nx && p.x <= (float)(nx + 1) && p.y >= (float)ny && p.y <= (float)(ny + 1)))
                     atomicOr(P.err, PBRT_E_NOT_PIXEL_MAJOR);
                 const float dx = p.x - 0.5f, dy = p.y - 0.5f;
                 // x in [ceil(dx - r), floor(dx + r)]  <=>  dx - r <= x <= dx + r for integer x
@@ -140,40 +141,62 @@ __device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
     return r;
 }
 
+// Row bytes of a sample: table row (ify, 0..15) of each of the 2h+1 window rows, one per byte,
+// 0xFF = the row is outside the sample's footprint.  1, 2 or 4 words so one LDS fetches them.
+template <int NW> struct RowBytes;
+template <> struct RowBytes<1> { typedef unsigned T; };
+template <> struct RowBytes<2> { typedef uint2 T; };
+template <> struct RowBytes<3> { typedef uint4 T; };
+
 template <int H>
 struct WinCfg {
     static constexpr int ROWS = 2 * H + 1;
     static constexpr int NW = (ROWS + 3) / 4;  // 32-bit words of packed row bytes per sample
+    typedef typename RowBytes<NW>::T RB;
 };
 
-// shared-memory layout for one sample row of a CTA strip
+constexpr int WIN_TABLE_BYTES = 2048;
+
+// shared-memory layout for one sample row of a CTA strip.  The pixel pitch is odd (in elements)
+// so that lanes reading sample s of consecutive pixels fall on distinct banks for 4/8/16-byte loads.
 template <int H, int TW>
 struct WinSmem {
     static constexpr int NPX = TW + 2 * H;
-    __host__ __device__ static int pitch_a(int spp) { return spp + 1; }                      // float4 units per pixel
-    __host__ __device__ static int pitch_b(int spp) { return (spp * WinCfg<H>::NW) | 1; }    // u32 units per pixel
+    __host__ __device__ static int pitch(int spp) { return spp | 1; }
     __host__ __device__ static size_t bytes(int spp) {
-        return 2048 + (size_t)NPX * pitch_a(spp) * 16 + (size_t)NPX * pitch_b(spp) * 4;
+        return WIN_TABLE_BYTES + (size_t)NPX * pitch(spp) * (16 + sizeof(typename WinCfg<H>::RB));
     }
 };
+
+__device__ __forceinline__ unsigned rb_word(unsigned v, int) { return v; }
+__device__ __forceinline__ unsigned rb_word(const uint2 &v, int k) { return k == 0 ? v.x : v.y; }
+__device__ __forceinline__ unsigned rb_word(const uint4 &v, int k) { return k == 0 ? v.x : (k == 1 ? v.y : v.z); }
+__device__ __forceinline__ void rb_make(unsigned &o, const unsigned *w) { o = w[0]; }
+__device__ __forceinline__ void rb_make(uint2 &o, const unsigned *w) { o = make_uint2(w[0], w[1]); }
+__device__ __forceinline__ void rb_make(uint4 &o, const unsigned *w) { o = make_uint4(w[0], w[1], w[2], 0u); }
+
+// float bits whose low byte is min(floor(|v|), 15): see table_index()
+__device__ __forceinline__ unsigned bin_bits(float v) {
+    return (unsigned)__float_as_int(__fadd_rd(fminf(fabsf(v), 15.f), 8388608.f));
+}
 
 template <int H, int TW, bool FMA>
 __global__ void __launch_bounds__(TW) splat_window_kernel(SplatParams P) {
     constexpr int ROWS = WinCfg<H>::ROWS;
     constexpr int NW = WinCfg<H>::NW;
+    typedef typename WinCfg<H>::RB RB;
     constexpr int NPX = WinSmem<H, TW>::NPX;
+    constexpr int TSHIFT = FMA ? 3 : 2;  // table entry: 4 B, or 8 B (w, w) so that one LDS.64 feeds FFMA2
     extern __shared__ __align__(16) unsigned char smem[];
-    // [0,2048): table with every weight stored twice, so one LDS.64 yields the (w, w) operand
-    float2 *s_tab = reinterpret_cast<float2 *>(smem);
-    float4 *s_a = reinterpret_cast<float4 *>(smem + 2048);
-    const int pitch_a = WinSmem<H, TW>::pitch_a(P.spp);
-    const int pitch_b = WinSmem<H, TW>::pitch_b(P.spp);
-    unsigned *s_b = reinterpret_cast<unsigned *>(smem + 2048 + (size_t)NPX * pitch_a * 16);
+    float4 *s_a = reinterpret_cast<float4 *>(smem + WIN_TABLE_BYTES);
+    const int pitch = WinSmem<H, TW>::pitch(P.spp);
+    RB *s_b = reinterpret_cast<RB *>(smem + WIN_TABLE_BYTES + (size_t)NPX * pitch * 16);
 
     const int tid = threadIdx.x;
     for (int i = tid; i < 256; i += TW) {
-        float w = P.table[i];
-        s_tab[i] = make_float2(w, w);
+        const float w = P.table[i];
+        if (FMA) reinterpret_cast<float2 *>(smem)[i] = make_float2(w, w);
+        else reinterpret_cast<float *>(smem)[i] = w;
     }
 
     const int cx0 = P.tb.x0 + blockIdx.x * TW;             // first output column of the strip
@@ -184,11 +207,15 @@ __global__ void __launch_bounds__(TW) splat_window_kernel(SplatParams P) {
     const float fx = (float)x;
     const int spp = P.spp;
     const int W = P.sb.x1 - P.sb.x0;
+    const bool clamp_on = P.max_lum < __int_as_float(0x7f800000);
 
-    // staged nominal pixels of a row: [sx0, sx1), local index = nx - (cx0 - H)
+    // staged nominal pixels of a row: [sx0, sx1); local index = nx - (cx0 - H)
     const int sx0 = max(cx0 - H, P.sb.x0), sx1 = min(cx0 + TW + H, P.sb.x1);
     const int nstaged = max(sx1 - sx0, 0) * spp;
-    const unsigned tab_addr = (unsigned)__cvta_generic_to_shared(s_tab);
+    // element e = tid + k*TW of the staged run is sample s of staged pixel q: advance (q, s) without dividing
+    const int q0 = tid / spp, r0 = tid - q0 * spp;
+    const int dq = TW / spp, dr = TW - dq * spp;
+    const int pl_base = sx0 - (cx0 - H);
 
     u64 acc_rg[ROWS], acc_bw[ROWS];
 #pragma unroll
@@ -200,35 +227,55 @@ __global__ void __launch_bounds__(TW) splat_window_kernel(SplatParams P) {
             __syncthreads();  // previous row fully consumed (also orders the table fill)
             // ---------------- pre-pass: one thread per sample of the row ----------------
             const size_t row_base = ((size_t)(ny - P.sb.y0) * W + (sx0 - P.sb.x0)) * (size_t)spp;
+            const float2 *gxy = P.xy + row_base;
+            const float4 *grgbw = P.rgbw + row_base;
             const float fny = (float)ny;
-            for (int e = tid; e < nstaged; e += TW) {
-                const float2 p = ldg_stream(&P.xy[row_base + e]);
-                float4 L = ldg_stream(&P.rgbw[row_base + e]);
-                const int pl_rel = e / spp;  // pixel within the staged run
-                const int s = e - pl_rel * spp;
-                const int nx = sx0 + pl_rel;
-                const float fnx = (float)nx;
-                if (!(p.x >= fnx && p.x < fnx + 1.f && p.y >= fny && p.y < fny + 1.f))
-                    atomicOr(P.err, PBRT_E_NOT_PIXEL_MAJOR);
-                clamp_luminance(L, P.max_lum);
-                const float pdx = p.x - 0.5f, pdy = p.y - 0.5f;
-                const float lo = pdy - P.ry, hi = pdy + P.ry;
-                unsigned words[NW];
+            int q = q0, sidx = r0;
+            constexpr int U = 4;  // samples per thread per trip: all loads issued before any is consumed
+            for (int e0 = tid; e0 < nstaged; e0 += U * TW) {
+                float2 p[U];
+                float4 L[U];
 #pragma unroll
-                for (int k = 0; k < NW; ++k) words[k] = 0;
-#pragma unroll
-                for (int j = 0; j < ROWS; ++j) {
-                    const float fr = fny + (float)(j - H);
-                    unsigned b = (unsigned)table_index((fr - pdy) * P.iry * 16.f) << 4;
-                    if (j == 0 || j == ROWS - 1) {  // only the outermost rows can fall outside
-                        if (!(fr >= lo && fr <= hi)) b = 0xFFu;
+                for (int u = 0; u < U; ++u) {
+                    if (e0 + u * TW < nstaged) {
+                        p[u] = ldg_stream(&gxy[e0 + u * TW]);
+                        L[u] = ldg_stream(&grgbw[e0 + u * TW]);
                     }
-                    words[j >> 2] |= b << (8 * (j & 3));
                 }
-                const int pl = nx - (cx0 - H);
-                s_a[pl * pitch_a + s] = make_float4(L.x * L.w, L.y * L.w, L.z * L.w, pdx);
 #pragma unroll
-                for (int k = 0; k < NW; ++k) s_b[pl * pitch_b + s * NW + k] = words[k];
+                for (int u = 0; u < U; ++u) {
+                    if (e0 + u * TW < nstaged) {
+                        const float fnx = (float)(sx0 + q);
+                        if (!(p[u].x >= fnx && p[u].x <= fnx + 1.f && p[u].y >= fny && p[u].y <= fny + 1.f))
+                            atomicOr(P.err, PBRT_E_NOT_PIXEL_MAJOR);
+                        if (clamp_on) clamp_luminance(L[u], P.max_lum);
+                        const float pdx = p[u].x - 0.5f, pdy = p[u].y - 0.5f;
+                        unsigned bits[ROWS];
+#pragma unroll
+                        for (int j = 0; j < ROWS; ++j) {
+                            const float fr = fny + (float)(j - H);
+                            bits[j] = bin_bits((fr - pdy) * P.iry * 16.f);
+                            // only the outermost rows can fall outside [ceil(pdy - r), floor(pdy + r)]
+                            if (j == 0 && !(fr >= pdy - P.ry)) bits[j] = 0xFFu;
+                            if (j == ROWS - 1 && !(fr <= pdy + P.ry)) bits[j] = 0xFFu;
+                        }
+                        unsigned words[NW];
+#pragma unroll
+                        for (int k = 0; k < NW; ++k) {
+                            const unsigned b0 = bits[4 * k];
+                            const unsigned b1 = 4 * k + 1 < ROWS ? bits[4 * k + 1] : 0u;
+                            const unsigned b2 = 4 * k + 2 < ROWS ? bits[4 * k + 2] : 0u;
+                            const unsigned b3 = 4 * k + 3 < ROWS ? bits[4 * k + 3] : 0u;
+                            words[k] = __byte_perm(__byte_perm(b0, b1, 0x0040), __byte_perm(b2, b3, 0x0040), 0x5410);
+                        }
+                        const int slot = (pl_base + q) * pitch + sidx;
+                        s_a[slot] = make_float4(L[u].x * L[u].w, L[u].y * L[u].w, L[u].z * L[u].w, pdx);
+                        rb_make(s_b[slot], words);
+                    }
+                    q += dq;
+                    sidx += dr;
+                    if (sidx >= spp) { sidx -= spp; ++q; }
+                }
             }
             __syncthreads();
             // ---------------- gather: this thread's column against the row ----------------
@@ -238,37 +285,34 @@ __global__ void __launch_bounds__(TW) splat_window_kernel(SplatParams P) {
                     const int nx = x + d;
                     if (nx < P.sb.x0 || nx >= P.sb.x1) continue;
                     const int pl = nx - (cx0 - H);
-                    const float4 *pa = s_a + pl * pitch_a;
-                    const unsigned *pbw = s_b + pl * pitch_b;
+                    const float4 *pa = s_a + pl * pitch;
+                    const RB *pb = s_b + pl * pitch;
 #pragma unroll 2
                     for (int s = 0; s < spp; ++s) {
-                        float4 a = pa[s];
-                        unsigned yw[NW];
-#pragma unroll
-                        for (int k = 0; k < NW; ++k) yw[k] = pbw[s * NW + k];
+                        const float4 a = pa[s];
+                        const RB yb = pb[s];
                         const float pdx = a.w;
                         // outermost columns: x must lie in [ceil(pdx - r), floor(pdx + r)]
                         if (d == H) { if (!(fx >= pdx - P.rx)) continue; }
                         if (d == -H) { if (!(fx <= pdx + P.rx)) continue; }
-                        const float t = fminf(fabsf((fx - pdx) * P.irx * 16.f), 15.f);
-                        // byte address of table column ifx in the duplicated table: ifx * 8
-                        const unsigned xaddr = tab_addr + ((unsigned)(__float_as_int(__fadd_rd(t, 8388608.f)) & 0xF) << 3);
+                        // byte offset of table column ifx
+                        const unsigned xoff = (bin_bits((fx - pdx) * P.irx * 16.f) & 0xFu) << TSHIFT;
                         const u64 Lrg = pack2(a.x, a.y);
                         const u64 Lb1 = pack2(a.z, 1.f);
 #pragma unroll
                         for (int j = 0; j < ROWS; ++j) {
-                            const unsigned b = __byte_perm(yw[j >> 2], 0, 0x4440 + (j & 3));
+                            const unsigned b = __byte_perm(rb_word(yb, j >> 2), 0, 0x4440 + (j & 3));
                             if (j == 0 || j == ROWS - 1) { if (b == 0xFFu) continue; }
+                            const unsigned char *wp = smem + (xoff + (b << (4 + TSHIFT)));
                             if (FMA) {
-                                u64 ww;
-                                asm volatile("ld.shared.b64 %0, [%1];" : "=l"(ww) : "r"(xaddr + (b << 3)));
+                                const float2 w2 = *reinterpret_cast<const float2 *>(wp);
+                                const u64 ww = pack2(w2.x, w2.y);
                                 acc_rg[j] = fma2(Lrg, ww, acc_rg[j]);
                                 acc_bw[j] = fma2(Lb1, ww, acc_bw[j]);
                             } else {
                                 // ptxas fuses mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even with --fmad=false,
                                 // so the products are formed by scalar FMULs and only the adds are packed.
-                                float w;
-                                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(w) : "r"(xaddr + (b << 3)));
+                                const float w = *reinterpret_cast<const float *>(wp);
                                 acc_rg[j] = add2(acc_rg[j], pack2(a.x * w, a.y * w));
                                 acc_bw[j] = add2(acc_bw[j], pack2(a.z * w, w));
                             }
@@ -315,7 +359,7 @@ __global__ void __launch_bounds__(256) splat_atomic_kernel(SplatParams P, int hx
             // lanes walk consecutive pixels: a 2-D strided read, spp*8 B apart
             const float2 p = P.xy[base + s];
             float4 L = P.rgbw[base + s];
-            if (!(p.x >= (float)nx && p.x < (float)(nx + 1) && p.y >= (float)ny && p.y < (float)(ny + 1)))
+            if (!(p.x >= (float)nx && p.x <= (float)(nx + 1) && p.y >= (float)ny && p.y <= (float)(ny + 1)))
                 atomicOr(P.err, PBRT_E_NOT_PIXEL_MAJOR);
             clamp_luminance(L, P.max_lum);
             const float dx = p.x - 0.5f, dy = p.y - 0.5f;
@@ -363,6 +407,11 @@ __global__ void __launch_bounds__(256) merge_scratch_kernel(float4 *__restrict__
 
 // ---- launch ------------------------------------------------------------------------------
 
+static int env_int(const char *name, int dflt) {
+    const char *v = getenv(name);
+    return v && *v ? atoi(v) : dflt;
+}
+
 template <int H, int TW, bool FMA>
 static int launch_window(const SplatParams &P0) {
     SplatParams P = P0;
@@ -373,13 +422,18 @@ static int launch_window(const SplatParams &P0) {
                                      227 * 1024));
         attr_set = true;
     }
+    int per_sm = 0;
+    PB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, splat_window_kernel<H, TW, FMA>, TW, smem));
+    if (per_sm < 1) return -1;
     const int cols = (bw(P.tb) + TW - 1) / TW;
     const int rows = bh(P.tb);
-    // aim for ~ (resident CTAs per SM) x SMs CTAs, but keep strips tall enough to amortise the halo rows
-    int per_sm = (int)std::max<size_t>(1, std::min<size_t>(2048 / TW, (227 * 1024) / smem));
-    int want = ctx().sm_count * per_sm;
-    int segs = std::max(1, std::min((want + cols - 1) / cols, (rows + 8 * H - 1) / (8 * H)));
-    P.rows_per_cta = (rows + segs - 1) / segs;
+    // One wave: at most as many CTAs as are resident at once (a ragged second wave would double the
+    // run time), but strips no shorter than 4h rows so the 2h halo rows stay a modest overhead.
+    const int resident = ctx().sm_count * per_sm;
+    int segs = std::max(1, resident / cols);
+    segs = std::min(segs, std::max(1, rows / (4 * H)));
+    int rpc = env_int("PBRT_B200_ROWS_PER_CTA", 0);
+    P.rows_per_cta = rpc > 0 ? rpc : (rows + segs - 1) / segs;
     segs = (rows + P.rows_per_cta - 1) / P.rows_per_cta;
     dim3 grid(cols, segs);
     splat_window_kernel<H, TW, FMA><<<grid, TW, smem, ctx().stream>>>(P);
@@ -390,6 +444,10 @@ static int launch_window(const SplatParams &P0) {
 template <int H, bool FMA>
 static int pick_width(const SplatParams &P) {
     // widest strip whose row of records leaves room for >= 2 CTAs per SM, else whatever fits
+    const int force = env_int("PBRT_B200_TW", 0);
+    if (force == 128) return launch_window<H, 128, FMA>(P);
+    if (force == 64) return launch_window<H, 64, FMA>(P);
+    if (force == 32) return launch_window<H, 32, FMA>(P);
     if (WinSmem<H, 128>::bytes(P.spp) * 2 <= 227 * 1024) return launch_window<H, 128, FMA>(P);
     if (WinSmem<H, 64>::bytes(P.spp) * 2 <= 227 * 1024) return launch_window<H, 64, FMA>(P);
     if (WinSmem<H, 32>::bytes(P.spp) <= 227 * 1024) return launch_window<H, 32, FMA>(P);

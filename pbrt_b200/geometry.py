@@ -41,6 +41,8 @@ class Bounds2i:
         """`Bounds2i::from([[x0,y0],[x1,y1]])` — sorts each axis (bounds.rs:119-130)."""
         if isinstance(b, Bounds2i):
             return b
+        if len(b) == 4:  # flat {x0, y0, x1, y1} as the C ABI passes bounds: taken as is
+            return Bounds2i.raw(*b)
         (ax, ay), (bx, by) = b
         return Bounds2i(Point2i(min(ax, bx), min(ay, by)), Point2i(max(ax, bx), max(ay, by)))
 

@@ -14,8 +14,15 @@ def init(device: int = 0) -> None:
 
 
 def set_stream(cuda_stream_ptr: int | None) -> None:
-    """Run subsequent work on a caller-owned cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream)."""
-    _lib.check(_lib.lib.pbrt_b200_set_stream(C.c_void_p(cuda_stream_ptr or 0)))
+    """Run subsequent work on a caller-owned cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream).
+
+    None selects the library's own stream.  A handle of 0 is CUDA's legacy default stream, which
+    the C ABI spells cudaStreamLegacy (0x1) because NULL there means "library stream".
+    """
+    if cuda_stream_ptr is None:
+        _lib.check(_lib.lib.pbrt_b200_set_stream(C.c_void_p(0)))
+    else:
+        _lib.check(_lib.lib.pbrt_b200_set_stream(C.c_void_p(int(cuda_stream_ptr) or 1)))
 
 
 def synchronize() -> None:
