@@ -41,7 +41,8 @@ typedef enum {
     PBRT_E_RANGE = 3,          /* point or bounds outside the film (reference: debug_assert / unwrap panic) */
     PBRT_E_NOT_PIXEL_MAJOR = 4,/* add_samples_tile: a sample lies outside its nominal pixel */
     PBRT_E_UNSUPPORTED = 5,
-    PBRT_E_NOMEM = 6
+    PBRT_E_NOMEM = 6,
+    PBRT_E_NONFINITE = 7       /* add_samples_tile: a sample's radiance * weight is not finite */
 } PbrtStatus;
 
 #define PBRT_FILTER_TABLE_WIDTH 16 /* src/core/film.rs:34 */
@@ -141,7 +142,9 @@ int pbrt_film_merge_tiles(PbrtFilm *film, int32_t ntiles, const int32_t *tile_bo
  * pixel (px,py) sits at index ((py-y0)*W + (px-x0))*spp + k and must lie in
  * [px,px+1] x [py,py+1] (closed: px + jitter may round up onto the next pixel boundary).  xy = 2 floats, rgbw = {L.r, L.g, L.b, sample_weight} per sample.
  * Per pixel the samples are accumulated in stream order, then converted and added to the film
- * exactly as merge_film_tile does.
+ * exactly as merge_film_tile does.  Radiance must be finite (pbrt zeroes non-finite samples before
+ * AddSample); violations of either contract are reported by pbrt_film_check and leave the film
+ * contents undefined.
  */
 enum { PBRT_SPLAT_EXACT = 0,   /* gather, mul then add: bit-identical to the CPU restatement */
        PBRT_SPLAT_FMA = 1,     /* gather, same order, fused multiply-add */

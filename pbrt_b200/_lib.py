@@ -13,7 +13,7 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 LIB_PATH = Path(os.environ.get("PBRT_B200_LIB", PKG / "lib" / "libpbrt_b200.so"))
 
-OK, E_INVALID, E_CUDA, E_RANGE, E_NOT_PIXEL_MAJOR, E_UNSUPPORTED, E_NOMEM = range(7)
+OK, E_INVALID, E_CUDA, E_RANGE, E_NOT_PIXEL_MAJOR, E_UNSUPPORTED, E_NOMEM, E_NONFINITE = range(8)
 FILTER_BOX, FILTER_TRIANGLE, FILTER_GAUSSIAN, FILTER_MITCHELL, FILTER_LANCZOS = range(5)
 SPLAT_EXACT, SPLAT_FMA, SPLAT_ATOMIC = range(3)
 

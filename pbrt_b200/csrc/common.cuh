@@ -14,6 +14,9 @@ namespace pb {
 
 struct Bounds { int x0, y0, x1, y1; };
 
+// bits of the film's sticky device-side error word (PbrtFilm::d_err), mapped to PbrtStatus by pbrt_film_check
+enum { ERRBIT_NOT_PIXEL_MAJOR = 1, ERRBIT_NONFINITE = 2 };
+
 __host__ __device__ inline int bw(const Bounds &b) { return b.x1 - b.x0; }
 __host__ __device__ inline int bh(const Bounds &b) { return b.y1 - b.y0; }
 

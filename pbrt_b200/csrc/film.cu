@@ -752,9 +752,11 @@ extern "C" int pbrt_film_check(PbrtFilm *f) {
     PB_CUDA(cudaStreamSynchronize(ctx().stream));
     if (e) {
         PB_CUDA(cudaMemsetAsync(f->d_err, 0, sizeof(int), ctx().stream));
-        if (e == PBRT_E_NOT_PIXEL_MAJOR)
-            return fail(e, "add_samples_tile: a sample lies outside its nominal pixel; film contents are undefined");
-        return fail(e, "asynchronous kernel error %d", e);
+        if (e & pb::ERRBIT_NOT_PIXEL_MAJOR)
+            return fail(PBRT_E_NOT_PIXEL_MAJOR, "add_samples_tile: a sample lies outside its nominal pixel; film contents are undefined");
+        if (e & pb::ERRBIT_NONFINITE)
+            return fail(PBRT_E_NONFINITE, "add_samples_tile: non-finite radiance; film contents are undefined");
+        return fail(PBRT_E_CUDA, "asynchronous kernel error word %d", e);
     }
     return PBRT_OK;
 }

@@ -47,6 +47,7 @@ struct SplatParams {
     float4 *film;
     int *err;
     int rows_per_cta;
+    unsigned negzero_bits;  // 0x80000000, passed at run time so ptxas cannot constant-fold it (see accumulate())
 };
 
 // ---- pieces shared by all variants -------------------------------------------------------
@@ -98,7 +99,7 @@ __global__ void __launch_bounds__(256) splat_gather_generic_kernel(SplatParams P
             for (int s = 0; s < P.spp; ++s) {
                 const float2 p = P.xy[base + s];
                 if (!(p.x >= (float)nx && p.x <= (float)(nx + 1) && p.y >= (float)ny && p.y <= (float)(ny + 1)))
-                    atomicOr(P.err, PBRT_E_NOT_PIXEL_MAJOR);
+                    atomicOr(P.err, ERRBIT_NOT_PIXEL_MAJOR);
                 const float dx = p.x - 0.5f, dy = p.y - 0.5f;
                 // x in [ceil(dx - r), floor(dx + r)]  <=>  dx - r <= x <= dx + r for integer x
                 if (!(fx >= dx - P.rx && fx <= dx + P.rx && fy >= dy - P.ry && fy <= dy + P.ry)) continue;
@@ -119,6 +120,11 @@ __global__ void __launch_bounds__(256) splat_gather_generic_kernel(SplatParams P
 }
 
 // ---- window gather -----------------------------------------------------------------------
+
+#ifndef PBRT_WIN_UNROLL
+#define PBRT_WIN_UNROLL 4
+#endif
+constexpr int kWinUnroll = PBRT_WIN_UNROLL;  // samples per trip of the gather's inner loop
 
 typedef unsigned long long u64;
 
@@ -141,8 +147,10 @@ __device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
     return r;
 }
 
-// Row bytes of a sample: table row (ify, 0..15) of each of the 2h+1 window rows, one per byte,
-// 0xFF = the row is outside the sample's footprint.  1, 2 or 4 words so one LDS fetches them.
+// Row bytes of a sample: for each of the ROWS = 2h+1 output rows of the window, the filter-table
+// row (ify, 0..15) it reads — or 16, the all-zero table row, when the sample's footprint does not
+// reach that row (only the two outermost rows can be unreachable).  One byte per row, 1..3 words,
+// fetched with one LDS.
 template <int NW> struct RowBytes;
 template <> struct RowBytes<1> { typedef unsigned T; };
 template <> struct RowBytes<2> { typedef uint2 T; };
@@ -151,11 +159,17 @@ template <> struct RowBytes<3> { typedef uint4 T; };
 template <int H>
 struct WinCfg {
     static constexpr int ROWS = 2 * H + 1;
-    static constexpr int NW = (ROWS + 3) / 4;  // 32-bit words of packed row bytes per sample
+    static constexpr int NW = (ROWS + 3) / 4;
     typedef typename RowBytes<NW>::T RB;
 };
 
-constexpr int WIN_TABLE_BYTES = 2048;
+// Filter table in shared memory: 17 rows x 17 entries of (w, w) — every weight twice, so one LDS.64
+// yields the packed operand.  Row 16 and column 16 are zero: a sample that does not reach a row /
+// column adds an exact zero there (x + 0 == x for every finite x), which keeps the inner loop free of
+// branches.  The odd row pitch also spreads equal columns of different rows over different banks.
+constexpr int TAB_ZERO = 16;
+constexpr int TAB_ROW_BYTES = 17 * 8;
+constexpr int WIN_TABLE_BYTES = 2432;  // >= 17 * TAB_ROW_BYTES, multiple of 128
 
 // shared-memory layout for one sample row of a CTA strip.  The pixel pitch is odd (in elements)
 // so that lanes reading sample s of consecutive pixels fall on distinct banks for 4/8/16-byte loads.
@@ -174,10 +188,29 @@ __device__ __forceinline__ unsigned rb_word(const uint4 &v, int k) { return k ==
 __device__ __forceinline__ void rb_make(unsigned &o, const unsigned *w) { o = w[0]; }
 __device__ __forceinline__ void rb_make(uint2 &o, const unsigned *w) { o = make_uint2(w[0], w[1]); }
 __device__ __forceinline__ void rb_make(uint4 &o, const unsigned *w) { o = make_uint4(w[0], w[1], w[2], 0u); }
+template <typename RB>
+__device__ __forceinline__ unsigned rb_byte(const RB &v, int i) {
+    return __byte_perm(rb_word(v, i >> 2), 0, 0x4440 + (i & 3));
+}
 
 // float bits whose low byte is min(floor(|v|), 15): see table_index()
 __device__ __forceinline__ unsigned bin_bits(float v) {
     return (unsigned)__float_as_int(__fadd_rd(fminf(fabsf(v), 15.f), 8388608.f));
+}
+
+__device__ __forceinline__ u64 lds_pair(unsigned addr) {
+    u64 v;
+    asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(addr));
+    return v;
+}
+
+// acc += L * (w, w).  Exact mode: the product is formed as fma(L, w, -0), which rounds exactly like a
+// multiply, with the -0 operand held in a register whose value ptxas cannot see (it would otherwise
+// fold fma+add or mul+add into a single FFMA2, which rounds once instead of twice).
+template <bool FMA>
+__device__ __forceinline__ u64 accumulate(u64 acc, u64 L, u64 ww, u64 negzero) {
+    if (FMA) return fma2(L, ww, acc);
+    return add2(acc, fma2(L, ww, negzero));
 }
 
 template <int H, int TW, bool FMA>
@@ -186,18 +219,22 @@ __global__ void __launch_bounds__(TW) splat_window_kernel(SplatParams P) {
     constexpr int NW = WinCfg<H>::NW;
     typedef typename WinCfg<H>::RB RB;
     constexpr int NPX = WinSmem<H, TW>::NPX;
-    constexpr int TSHIFT = FMA ? 3 : 2;  // table entry: 4 B, or 8 B (w, w) so that one LDS.64 feeds FFMA2
     extern __shared__ __align__(16) unsigned char smem[];
     float4 *s_a = reinterpret_cast<float4 *>(smem + WIN_TABLE_BYTES);
     const int pitch = WinSmem<H, TW>::pitch(P.spp);
     RB *s_b = reinterpret_cast<RB *>(smem + WIN_TABLE_BYTES + (size_t)NPX * pitch * 16);
 
     const int tid = threadIdx.x;
-    for (int i = tid; i < 256; i += TW) {
-        const float w = P.table[i];
-        if (FMA) reinterpret_cast<float2 *>(smem)[i] = make_float2(w, w);
-        else reinterpret_cast<float *>(smem)[i] = w;
+    for (int i = tid; i < 17 * 17; i += TW) {
+        const int ty = i / 17, tx = i - ty * 17;
+        const float w = (ty < 16 && tx < 16) ? P.table[ty * 16 + tx] : 0.f;
+        *reinterpret_cast<float2 *>(smem + ty * TAB_ROW_BYTES + tx * 8) = make_float2(w, w);
     }
+    // shared-window address of the table, kept opaque so it lives in a register instead of being
+    // rematerialised (S2UR/ULEA) at every use
+    unsigned tab_base = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("mov.u32 %0, %0;" : "+r"(tab_base));
+    const u64 negzero = ((u64)P.negzero_bits << 32) | P.negzero_bits;
 
     const int cx0 = P.tb.x0 + blockIdx.x * TW;             // first output column of the strip
     const int cy0 = P.tb.y0 + blockIdx.y * P.rows_per_cta; // first output row
@@ -207,7 +244,8 @@ __global__ void __launch_bounds__(TW) splat_window_kernel(SplatParams P) {
     const float fx = (float)x;
     const int spp = P.spp;
     const int W = P.sb.x1 - P.sb.x0;
-    const bool clamp_on = P.max_lum < __int_as_float(0x7f800000);
+    const float inf = __int_as_float(0x7f800000);
+    const bool clamp_on = P.max_lum < inf;
 
     // staged nominal pixels of a row: [sx0, sx1); local index = nx - (cx0 - H)
     const int sx0 = max(cx0 - H, P.sb.x0), sx1 = min(cx0 + TW + H, P.sb.x1);
@@ -246,30 +284,28 @@ __global__ void __launch_bounds__(TW) splat_window_kernel(SplatParams P) {
                 for (int u = 0; u < U; ++u) {
                     if (e0 + u * TW < nstaged) {
                         const float fnx = (float)(sx0 + q);
-                        if (!(p[u].x >= fnx && p[u].x <= fnx + 1.f && p[u].y >= fny && p[u].y <= fny + 1.f))
-                            atomicOr(P.err, PBRT_E_NOT_PIXEL_MAJOR);
                         if (clamp_on) clamp_luminance(L[u], P.max_lum);
+                        const float cr = L[u].x * L[u].w, cg = L[u].y * L[u].w, cb = L[u].z * L[u].w;
+                        // contract: the sample lies in its nominal pixel (closed) and its radiance is finite
+                        if (!(p[u].x >= fnx && p[u].x <= fnx + 1.f && p[u].y >= fny && p[u].y <= fny + 1.f))
+                            atomicOr(P.err, ERRBIT_NOT_PIXEL_MAJOR);
+                        if (!(fabsf(cr) + fabsf(cg) + fabsf(cb) < inf)) atomicOr(P.err, ERRBIT_NONFINITE);
                         const float pdx = p[u].x - 0.5f, pdy = p[u].y - 0.5f;
-                        unsigned bits[ROWS];
+                        unsigned bits[12];
 #pragma unroll
-                        for (int j = 0; j < ROWS; ++j) {
-                            const float fr = fny + (float)(j - H);
-                            bits[j] = bin_bits((fr - pdy) * P.iry * 16.f);
-                            // only the outermost rows can fall outside [ceil(pdy - r), floor(pdy + r)]
-                            if (j == 0 && !(fr >= pdy - P.ry)) bits[j] = 0xFFu;
-                            if (j == ROWS - 1 && !(fr <= pdy + P.ry)) bits[j] = 0xFFu;
-                        }
+                        for (int j = 0; j < ROWS; ++j) bits[j] = bin_bits((fny + (float)(j - H) - pdy) * P.iry * 16.f);
+#pragma unroll
+                        for (int j = ROWS; j < 12; ++j) bits[j] = 0u;
+                        // only the outermost rows can fall outside [ceil(pdy - r), floor(pdy + r)]
+                        if (!(fny - (float)H >= pdy - P.ry)) bits[0] = TAB_ZERO;
+                        if (!(fny + (float)H <= pdy + P.ry)) bits[ROWS - 1] = TAB_ZERO;
                         unsigned words[NW];
 #pragma unroll
-                        for (int k = 0; k < NW; ++k) {
-                            const unsigned b0 = bits[4 * k];
-                            const unsigned b1 = 4 * k + 1 < ROWS ? bits[4 * k + 1] : 0u;
-                            const unsigned b2 = 4 * k + 2 < ROWS ? bits[4 * k + 2] : 0u;
-                            const unsigned b3 = 4 * k + 3 < ROWS ? bits[4 * k + 3] : 0u;
-                            words[k] = __byte_perm(__byte_perm(b0, b1, 0x0040), __byte_perm(b2, b3, 0x0040), 0x5410);
-                        }
+                        for (int k = 0; k < NW; ++k)
+                            words[k] = __byte_perm(__byte_perm(bits[4 * k], bits[4 * k + 1], 0x0040),
+                                                   __byte_perm(bits[4 * k + 2], bits[4 * k + 3], 0x0040), 0x5410);
                         const int slot = (pl_base + q) * pitch + sidx;
-                        s_a[slot] = make_float4(L[u].x * L[u].w, L[u].y * L[u].w, L[u].z * L[u].w, pdx);
+                        s_a[slot] = make_float4(cr, cg, cb, pdx);
                         rb_make(s_b[slot], words);
                     }
                     q += dq;
@@ -278,6 +314,14 @@ __global__ void __launch_bounds__(TW) splat_window_kernel(SplatParams P) {
                 }
             }
             __syncthreads();
+            // pull the next sample row of this strip into L2 while this one is gathered, so that its
+            // pre-pass loads pay L2 latency instead of DRAM latency
+            if (ny + 1 < P.sb.y1 && ny + 1 < cy1 + H) {
+                const char *nxy = reinterpret_cast<const char *>(gxy + (size_t)W * spp);
+                const char *nrgbw = reinterpret_cast<const char *>(grgbw + (size_t)W * spp);
+                for (int o = tid * 128; o < nstaged * 8; o += TW * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(nxy + o));
+                for (int o = tid * 128; o < nstaged * 16; o += TW * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(nrgbw + o));
+            }
             // ---------------- gather: this thread's column against the row ----------------
             if (col_ok) {
 #pragma unroll
@@ -287,34 +331,36 @@ __global__ void __launch_bounds__(TW) splat_window_kernel(SplatParams P) {
                     const int pl = nx - (cx0 - H);
                     const float4 *pa = s_a + pl * pitch;
                     const RB *pb = s_b + pl * pitch;
-#pragma unroll 2
+#pragma unroll kWinUnroll
                     for (int s = 0; s < spp; ++s) {
                         const float4 a = pa[s];
                         const RB yb = pb[s];
                         const float pdx = a.w;
-                        // outermost columns: x must lie in [ceil(pdx - r), floor(pdx + r)]
-                        if (d == H) { if (!(fx >= pdx - P.rx)) continue; }
-                        if (d == -H) { if (!(fx <= pdx + P.rx)) continue; }
-                        // byte offset of table column ifx
-                        const unsigned xoff = (bin_bits((fx - pdx) * P.irx * 16.f) & 0xFu) << TSHIFT;
+                        unsigned ifx = bin_bits((fx - pdx) * P.irx * 16.f) & 0xFu;
+                        // Outermost columns: x must lie in [ceil(pdx - r), floor(pdx + r)].  Lanes hold sample
+                        // s of neighbouring pixels, which for stratified streams sit in the same stratum and
+                        // agree: vote and skip the sample for the whole warp when no lane needs it; a lane
+                        // that does not need it reads the zero column.
+                        if (d == H || d == -H) {
+                            const bool reach = d == H ? fx >= pdx - P.rx : fx <= pdx + P.rx;
+                            if (!__any_sync(__activemask(), reach)) continue;
+                            ifx = reach ? ifx : TAB_ZERO;
+                        }
+                        const unsigned xcol = tab_base + (ifx << 3);  // shared address of table column ifx
                         const u64 Lrg = pack2(a.x, a.y);
                         const u64 Lb1 = pack2(a.z, 1.f);
 #pragma unroll
                         for (int j = 0; j < ROWS; ++j) {
-                            const unsigned b = __byte_perm(rb_word(yb, j >> 2), 0, 0x4440 + (j & 3));
-                            if (j == 0 || j == ROWS - 1) { if (b == 0xFFu) continue; }
-                            const unsigned char *wp = smem + (xoff + (b << (4 + TSHIFT)));
+                            const u64 ww = lds_pair(xcol + rb_byte(yb, j) * TAB_ROW_BYTES);
+                            acc_rg[j] = accumulate<FMA>(acc_rg[j], Lrg, ww, negzero);
                             if (FMA) {
-                                const float2 w2 = *reinterpret_cast<const float2 *>(wp);
-                                const u64 ww = pack2(w2.x, w2.y);
-                                acc_rg[j] = fma2(Lrg, ww, acc_rg[j]);
                                 acc_bw[j] = fma2(Lb1, ww, acc_bw[j]);
                             } else {
-                                // ptxas fuses mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even with --fmad=false,
-                                // so the products are formed by scalar FMULs and only the adds are packed.
-                                const float w = *reinterpret_cast<const float *>(wp);
-                                acc_rg[j] = add2(acc_rg[j], pack2(a.x * w, a.y * w));
-                                acc_bw[j] = add2(acc_bw[j], pack2(a.z * w, w));
+                                // (b*w, w): the product overwrites the low half of the loaded (w, w) pair in place,
+                                // so no (b, 1) operand has to be rebuilt per row
+                                float w0, w1;
+                                unpack2(ww, w0, w1);
+                                acc_bw[j] = add2(acc_bw[j], pack2(a.z * w0, w1));
                             }
                         }
                     }
@@ -360,7 +406,7 @@ __global__ void __launch_bounds__(256) splat_atomic_kernel(SplatParams P, int hx
             const float2 p = P.xy[base + s];
             float4 L = P.rgbw[base + s];
             if (!(p.x >= (float)nx && p.x <= (float)(nx + 1) && p.y >= (float)ny && p.y <= (float)(ny + 1)))
-                atomicOr(P.err, PBRT_E_NOT_PIXEL_MAJOR);
+                atomicOr(P.err, ERRBIT_NOT_PIXEL_MAJOR);
             clamp_luminance(L, P.max_lum);
             const float dx = p.x - 0.5f, dy = p.y - 0.5f;
             const int p0x = max(max(__float2int_ru(dx - P.rx), P.tb.x0), ox);
@@ -480,6 +526,7 @@ int launch_splat_tile(PbrtFilm *f, const Bounds &sb, const Bounds &tb, int spp, 
     P.film = f->d_xyzw;
     P.err = f->d_err;
     P.rows_per_cta = 0;
+    P.negzero_bits = 0x80000000u;
     if (!(P.rx > 0.f) || !(P.ry > 0.f) || P.rx > 1024.f || P.ry > 1024.f)
         return fail(PBRT_E_UNSUPPORTED, "filter radius (%g, %g) outside (0, 1024]", P.rx, P.ry);
     // a sample in nominal pixel n reaches pixels n - h .. n + h, h = floor(r + .5)

@@ -42,7 +42,10 @@ def test_library_is_sm100a_only(pb):
 
 
 def test_exact_splat_kernel_has_no_fused_accumulate(pb):
-    """ptxas fuses f32x2 mul+add even with --fmad=false; the exact kernel must not contain FFMA2."""
+    """ptxas fuses f32x2 mul+add into one FFMA2 even with --fmad=false (one rounding instead of two).
+    The exact kernel therefore forms products as fma(L, w, -0) with -0 in a register ptxas cannot see,
+    and adds separately: every FFMA2 in it must take that scalar register (".F32") as its addend, and
+    every product must be followed by a packed add."""
     from pbrt_b200 import _lib
 
     sass = subprocess.run(["cuobjdump", "-sass", str(_lib.LIB_PATH)], capture_output=True, text=True).stdout
@@ -50,11 +53,17 @@ def test_exact_splat_kernel_has_no_fused_accumulate(pb):
     checked = 0
     for b in blocks:
         name = b.split("\n", 1)[0]
-        if "splat_window_kernel" in name and "Lb0E" in name:
-            assert "FFMA2" not in b and "FADD2" in b, name
+        if "splat_window_kernel" not in name:
+            continue
+        ffma2 = re.findall(r"FFMA2 [^;]*;", b)
+        fadd2 = re.findall(r"FADD2 [^;]*;", b)
+        if "Lb0E" in name:  # exact
+            assert ffma2 and len(fadd2) >= len(ffma2), name
+            for ins in ffma2:
+                assert re.search(r", U?R\d+\.F32 ;$", ins), f"{name}: fused accumulate {ins}"
             checked += 1
-        if "splat_window_kernel" in name and "Lb1E" in name:
-            assert "FFMA2" in b, name
+        else:  # fma mode accumulates with the fused form
+            assert any(re.search(r"\.F32x2\.HI_LO ;$", ins) for ins in ffma2), name
     assert checked >= 4
 
 
