@@ -54,6 +54,17 @@ WORKLOADS = {
 FILTER_KIND = {"box": 0, "triangle": 1, "gaussian": 2, "mitchell": 3, "lanczos": 4}
 
 
+def measured_traffic(workload: str, mode: str):
+    """DRAM bytes per launch of the splat kernel from the committed ncu capture (profiles/traffic.json)."""
+    p = ROOT / "profiles" / "traffic.json"
+    if p.exists():
+        try:
+            return json.loads(p.read_text()).get(f"{workload}:{mode}")
+        except Exception:
+            pass
+    return None
+
+
 def measured_peak_gbs():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -67,7 +78,7 @@ def measured_peak_gbs():
 class ClockSampler(threading.Thread):
     """nvidia-smi style clock / throttle-reason samples during the timed region (via NVML)."""
 
-    def __init__(self, index: int, period: float = 0.05):
+    def __init__(self, index: int, period: float = 0.004):
         super().__init__(daemon=True)
         self.index, self.period = index, period
         self.samples, self.reasons, self.max_mhz = [], set(), None
@@ -188,8 +199,8 @@ def run_reference(args, wl, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--mode", default="exact", choices=["exact", "fma", "atomic"])
@@ -294,7 +305,7 @@ def main():
     achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
     roofline = {
         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-        "traffic": None, "peak_source": peak_src, "kernel": "splat_window_kernel" if args.mode != "atomic" else "splat_atomic_kernel",
+        "traffic": measured_traffic(args.workload, args.mode) if world == 1 else None, "peak_source": peak_src, "kernel": "splat_window_kernel" if args.mode != "atomic" else "splat_atomic_kernel",
         "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kern_ms, "kernel_ms_min": min(per_step),
         "note": "24 B/sample read + 32 B/film pixel RMW per launch; the kernel is issue-bound, not HBM-bound (DESIGN.md)",
     }
