@@ -100,6 +100,17 @@ struct PbrtFilm {
     size_t stage_bytes[2];
     float4 *d_scratch_tile;  // add_samples (arbitrary order) scratch
     size_t scratch_tile_px;
+    // merge_tiles: the per-cell tile index of the last batch, reused while the tiling repeats
+    // (a renderer merges the same tile grid every pass)
+    int32_t *idx_bounds;     // host copy of the batch's tile bounds (4 per tile)
+    int64_t *idx_offsets;    // host copy of the batch's pixel offsets
+    int idx_ntiles;
+    void *d_idx;             // device blob [cell_start | cell_tiles | tile bounds | tile offsets]
+    size_t d_idx_bytes;
+    pb::Bounds idx_box;
+    int idx_cells_x;
+    size_t idx_off[4];
+    int64_t idx_need;        // pixels the batch's rgbw buffer must hold
 };
 
 namespace pb {

@@ -354,6 +354,9 @@ extern "C" int pbrt_film_destroy(PbrtFilm *f) {
     cudaFree(f->d_stage[0]);
     cudaFree(f->d_stage[1]);
     cudaFree(f->d_scratch_tile);
+    cudaFree(f->d_idx);
+    free(f->idx_bounds);
+    free(f->idx_offsets);
     cudaGetLastError();
     delete f;
     return PBRT_OK;
@@ -513,53 +516,83 @@ extern "C" int pbrt_film_merge_tiles(PbrtFilm *f, int32_t ntiles, const int32_t 
     if (!f) return fail(PBRT_E_INVALID, "null film");
     if (ntiles <= 0) return PBRT_OK;
     if (!tbs || !offsets || !rgbw) return fail(PBRT_E_INVALID, "null argument");
-    // union box and range checks
-    Bounds box{INT32_MAX, INT32_MAX, INT32_MIN, INT32_MIN};
-    std::vector<int4> tb(ntiles);
-    std::vector<long long> off(ntiles);
-    bool any = false;
-    for (int i = 0; i < ntiles; ++i) {
-        Bounds b{tbs[4 * i], tbs[4 * i + 1], tbs[4 * i + 2], tbs[4 * i + 3]};
-        off[i] = offsets[i];
-        if (b.x1 <= b.x0 || b.y1 <= b.y0) { tb[i] = make_int4(0, 0, 0, 0); continue; }
-        if (!inside(f->owned, b)) return fail(PBRT_E_RANGE, "tile %d outside the film", i);
-        if (offsets[i] < 0 || offsets[i] + (int64_t)pb::bw(b) * pb::bh(b) > total_pixels)
-            return fail(PBRT_E_INVALID, "tile %d: pixels outside the rgbw buffer", i);
-        tb[i] = make_int4(b.x0, b.y0, b.x1, b.y1);
-        box.x0 = std::min(box.x0, b.x0); box.y0 = std::min(box.y0, b.y0);
-        box.x1 = std::max(box.x1, b.x1); box.y1 = std::max(box.y1, b.y1);
-        any = true;
+    const bool cached = f->d_idx && f->idx_ntiles == ntiles &&
+                        memcmp(f->idx_bounds, tbs, (size_t)ntiles * 4 * sizeof(int32_t)) == 0 &&
+                        memcmp(f->idx_offsets, offsets, (size_t)ntiles * sizeof(int64_t)) == 0;
+    if (!cached) {
+        // union box and range checks
+        Bounds box{INT32_MAX, INT32_MAX, INT32_MIN, INT32_MIN};
+        std::vector<int4> tb(ntiles);
+        std::vector<long long> off(ntiles);
+        bool any = false;
+        int64_t need = 0;
+        for (int i = 0; i < ntiles; ++i) {
+            Bounds b{tbs[4 * i], tbs[4 * i + 1], tbs[4 * i + 2], tbs[4 * i + 3]};
+            off[i] = offsets[i];
+            if (b.x1 <= b.x0 || b.y1 <= b.y0) { tb[i] = make_int4(0, 0, 0, 0); continue; }
+            if (!inside(f->owned, b)) return fail(PBRT_E_RANGE, "tile %d outside the film", i);
+            if (offsets[i] < 0 || offsets[i] + (int64_t)pb::bw(b) * pb::bh(b) > total_pixels)
+                return fail(PBRT_E_INVALID, "tile %d: pixels outside the rgbw buffer", i);
+            tb[i] = make_int4(b.x0, b.y0, b.x1, b.y1);
+            need = std::max<int64_t>(need, offsets[i] + (int64_t)pb::bw(b) * pb::bh(b));
+            box.x0 = std::min(box.x0, b.x0); box.y0 = std::min(box.y0, b.y0);
+            box.x1 = std::max(box.x1, b.x1); box.y1 = std::max(box.y1, b.y1);
+            any = true;
+        }
+        if (!any) return PBRT_OK;
+        // CSR of tiles per 16x16 cell, ascending tile index
+        const int cx = (pb::bw(box) + 15) / 16, cy = (pb::bh(box) + 15) / 16;
+        std::vector<int> start((size_t)cx * cy + 1, 0);
+        for (int i = 0; i < ntiles; ++i) {
+            if (tb[i].z <= tb[i].x) continue;
+            for (int gy = (tb[i].y - box.y0) >> 4; gy <= (tb[i].w - 1 - box.y0) >> 4; ++gy)
+                for (int gx = (tb[i].x - box.x0) >> 4; gx <= (tb[i].z - 1 - box.x0) >> 4; ++gx) start[(size_t)gy * cx + gx + 1]++;
+        }
+        for (size_t c = 0; c < (size_t)cx * cy; ++c) start[c + 1] += start[c];
+        std::vector<int> fill(start.begin(), start.end() - 1);
+        std::vector<int> list((size_t)start.back());
+        for (int i = 0; i < ntiles; ++i) {
+            if (tb[i].z <= tb[i].x) continue;
+            for (int gy = (tb[i].y - box.y0) >> 4; gy <= (tb[i].w - 1 - box.y0) >> 4; ++gy)
+                for (int gx = (tb[i].x - box.x0) >> 4; gx <= (tb[i].z - 1 - box.x0) >> 4; ++gx) list[(size_t)fill[(size_t)gy * cx + gx]++] = i;
+        }
+        // one upload: [start | list | bounds | offsets], each part 16-byte aligned
+        auto align16 = [](size_t v) { return (v + 15) & ~size_t(15); };
+        const size_t b0 = 0, b1 = align16(start.size() * sizeof(int)), b2 = b1 + align16(list.size() * sizeof(int));
+        const size_t b3 = b2 + tb.size() * sizeof(int4), b4 = b3 + off.size() * sizeof(long long);
+        std::vector<unsigned char> blob(b4);
+        memcpy(&blob[b0], start.data(), start.size() * sizeof(int));
+        if (!list.empty()) memcpy(&blob[b1], list.data(), list.size() * sizeof(int));
+        memcpy(&blob[b2], tb.data(), tb.size() * sizeof(int4));
+        memcpy(&blob[b3], off.data(), off.size() * sizeof(long long));
+        if (blob.size() > f->d_idx_bytes) {
+            cudaFree(f->d_idx);
+            f->d_idx = nullptr;
+            f->d_idx_bytes = 0;
+            PB_CUDA(cudaMalloc(&f->d_idx, blob.size() + 256));
+            f->d_idx_bytes = blob.size() + 256;
+        }
+        f->idx_ntiles = 0;  // invalid until everything below succeeded
+        PB_CUDA(cudaMemcpyAsync(f->d_idx, blob.data(), blob.size(), cudaMemcpyHostToDevice, ctx().stream));
+        PB_CUDA(cudaStreamSynchronize(ctx().stream));  // blob is a local
+        free(f->idx_bounds);
+        free(f->idx_offsets);
+        f->idx_bounds = (int32_t *)malloc((size_t)ntiles * 4 * sizeof(int32_t));
+        f->idx_offsets = (int64_t *)malloc((size_t)ntiles * sizeof(int64_t));
+        if (!f->idx_bounds || !f->idx_offsets) return fail(PBRT_E_NOMEM, "host allocation failed");
+        memcpy(f->idx_bounds, tbs, (size_t)ntiles * 4 * sizeof(int32_t));
+        memcpy(f->idx_offsets, offsets, (size_t)ntiles * sizeof(int64_t));
+        f->idx_box = box;
+        f->idx_cells_x = cx;
+        f->idx_off[0] = b0; f->idx_off[1] = b1; f->idx_off[2] = b2; f->idx_off[3] = b3;
+        f->idx_need = need;
+        f->idx_ntiles = ntiles;
     }
-    if (!any) return PBRT_OK;
-    // CSR of tiles per 16x16 cell, ascending tile index
-    const int cx = (pb::bw(box) + 15) / 16, cy = (pb::bh(box) + 15) / 16;
-    std::vector<int> start((size_t)cx * cy + 1, 0);
-    for (int i = 0; i < ntiles; ++i) {
-        if (tb[i].z <= tb[i].x) continue;
-        for (int gy = (tb[i].y - box.y0) >> 4; gy <= (tb[i].w - 1 - box.y0) >> 4; ++gy)
-            for (int gx = (tb[i].x - box.x0) >> 4; gx <= (tb[i].z - 1 - box.x0) >> 4; ++gx) start[(size_t)gy * cx + gx + 1]++;
-    }
-    for (size_t c = 0; c < (size_t)cx * cy; ++c) start[c + 1] += start[c];
-    std::vector<int> fill(start.begin(), start.end() - 1);
-    std::vector<int> list((size_t)start.back());
-    for (int i = 0; i < ntiles; ++i) {
-        if (tb[i].z <= tb[i].x) continue;
-        for (int gy = (tb[i].y - box.y0) >> 4; gy <= (tb[i].w - 1 - box.y0) >> 4; ++gy)
-            for (int gx = (tb[i].x - box.x0) >> 4; gx <= (tb[i].z - 1 - box.x0) >> 4; ++gx) list[(size_t)fill[(size_t)gy * cx + gx]++] = i;
-    }
-    // one upload: [start | list | bounds | offsets]
-    size_t b0 = 0, b1 = b0 + start.size() * sizeof(int), b2 = b1 + ((list.size() * sizeof(int) + 15) & ~size_t(15));
-    b1 = (b1 + 15) & ~size_t(15);
-    b2 = b1 + ((list.size() * sizeof(int) + 15) & ~size_t(15));
-    size_t b3 = b2 + tb.size() * sizeof(int4), b4 = b3 + off.size() * sizeof(long long);
-    std::vector<unsigned char> blob(b4);
-    memcpy(&blob[b0], start.data(), start.size() * sizeof(int));
-    if (!list.empty()) memcpy(&blob[b1], list.data(), list.size() * sizeof(int));
-    memcpy(&blob[b2], tb.data(), tb.size() * sizeof(int4));
-    memcpy(&blob[b3], off.data(), off.size() * sizeof(long long));
-    void *d_blob;
-    if (int rc = pb::stage_in(f, 1, blob.data(), blob.size(), &d_blob)) return rc;
-    PB_CUDA(cudaStreamSynchronize(ctx().stream));  // blob is a local
+    if (total_pixels < f->idx_need) return fail(PBRT_E_INVALID, "rgbw buffer smaller than the tiles it must hold");
+    const Bounds box = f->idx_box;
+    void *d_blob = f->d_idx;
+    const size_t b0 = f->idx_off[0], b1 = f->idx_off[1], b2 = f->idx_off[2], b3 = f->idx_off[3];
+    const int cx = f->idx_cells_x;
     const float4 *d_tiles = (const float4 *)rgbw;
     if (!src_is_device) {
         void *d;
@@ -598,19 +631,25 @@ __device__ __forceinline__ void resolve_pixel(float4 p, float sx, float sy, floa
     r *= scale; g *= scale; b *= scale;
 }
 
-// src/lib.rs:93-99 + src/core/imageio.rs:66-68.  powf is evaluated in f32 first; when the result
-// sits within 1e-3 of a byte boundary it is redone through f64 pow so the byte agrees with a
+// src/lib.rs:93-99 + src/core/imageio.rs:66-68.  The byte only changes when 255*g + .5 crosses an
+// integer, so powf is evaluated in three tiers: the MUFU approximation (exp2(y*log2 x), a few 1e-6
+// relative) decides every value further than 4e-3 from a byte boundary; closer values are redone with
+// CUDA's accurate powf, and those still within 1e-3 through f64 pow, so that the byte agrees with a
 // correctly rounded f32 powf (what glibc's powf delivers for the CPU path).
 __device__ __forceinline__ unsigned char to_byte(float v) {
     float g;
     if (v <= 0.0031308f) {
         g = 12.92f * v;
     } else {
-        g = 1.055f * powf(v, 1.f / 2.4f) - 0.055f;
+        g = 1.055f * __powf(v, 1.f / 2.4f) - 0.055f;
         float t = 255.f * g + 0.5f;
-        if (fabsf(t - rintf(t)) < 1e-3f) {
-            float p = (float)pow((double)v, (double)(1.f / 2.4f));
-            g = 1.055f * p - 0.055f;
+        if (!(fabsf(t - rintf(t)) >= 4e-3f) && t > -1.f && t < 257.f) {
+            g = 1.055f * powf(v, 1.f / 2.4f) - 0.055f;
+            t = 255.f * g + 0.5f;
+            if (fabsf(t - rintf(t)) < 1e-3f) {
+                float p = (float)pow((double)v, (double)(1.f / 2.4f));
+                g = 1.055f * p - 0.055f;
+            }
         }
     }
     float c = 255.f * g + 0.5f;
@@ -968,12 +1007,11 @@ __global__ void __launch_bounds__(256) fill_rgb_kernel(float *__restrict__ out, 
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
     unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < head) out[i] = c[i % 3];
-    // phase of the first float of vector k is (head + 4k) % 3; the three possible vectors:
-    float4 pat[3];
-    pat[0] = make_float4(r, g, b, r);
-    pat[1] = make_float4(g, b, r, g);
-    pat[2] = make_float4(b, r, g, b);
-    for (; i < nvec; i += stride) pb::stg_stream(&body[i], pat[(head + 4 * i) % 3]);
+    // The phase of the first float of vector k is (head + 4k) % 3 = (head + k) % 3.  The launch uses a
+    // multiple of 3 threads, so a thread's phase never changes as it strides: pick its vector once.
+    const unsigned phase = (unsigned)((head + i) % 3);
+    const float4 v = phase == 0 ? make_float4(r, g, b, r) : (phase == 1 ? make_float4(g, b, r, g) : make_float4(b, r, g, b));
+    for (; i < nvec; i += stride) pb::stg_stream(&body[i], v);
     const unsigned long long done = head + nvec * 4;
     i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (done + i < nf) out[done + i] = c[(done + i) % 3];
@@ -1008,7 +1046,8 @@ extern "C" int pbrt_texture_constant_eval_rgb(const float value[3], uint64_t n, 
     void *d_out = out;
     if (!dst_is_device)
         if (int rc = pb::out_stage(n * 3 * sizeof(float), &d_out)) return rc;
-    fill_rgb_kernel<<<fill_grid(n * 3 / 4), 256, 0, ctx().stream>>>((float *)d_out, n, value[0], value[1], value[2]);
+    const int blocks3 = (fill_grid(n * 3 / 4) + 2) / 3 * 3;  // thread count divisible by 3: see the kernel
+    fill_rgb_kernel<<<blocks3, 256, 0, ctx().stream>>>((float *)d_out, n, value[0], value[1], value[2]);
     PB_LAUNCH_CHECK("fill_rgb_kernel");
     if (!dst_is_device) {
         PB_CUDA(cudaMemcpyAsync(out, d_out, n * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx().stream));
