@@ -198,9 +198,12 @@ __device__ __forceinline__ unsigned bin_bits(float v) {
     return (unsigned)__float_as_int(__fadd_rd(fminf(fabsf(v), 15.f), 8388608.f));
 }
 
+// Table fetch.  Deliberately not `volatile`: the table is constant once the kernel's first barrier has
+// passed and the address depends on data read after it, so the compiler may schedule these loads
+// early across the unrolled samples without being able to hoist them too far.
 __device__ __forceinline__ u64 lds_pair(unsigned addr) {
     u64 v;
-    asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(addr));
+    asm("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(addr));
     return v;
 }
 
@@ -246,6 +249,8 @@ __global__ void __launch_bounds__(TW) splat_window_kernel(SplatParams P) {
     const int W = P.sb.x1 - P.sb.x0;
     const float inf = __int_as_float(0x7f800000);
     const bool clamp_on = P.max_lum < inf;
+    // (d * inv_radius) * 16 == d * (inv_radius * 16) bit for bit: scaling by a power of two commutes with rounding
+    const float irx16 = P.irx * 16.f, iry16 = P.iry * 16.f;
 
     // staged nominal pixels of a row: [sx0, sx1); local index = nx - (cx0 - H)
     const int sx0 = max(cx0 - H, P.sb.x0), sx1 = min(cx0 + TW + H, P.sb.x1);
@@ -293,7 +298,7 @@ __global__ void __launch_bounds__(TW) splat_window_kernel(SplatParams P) {
                         const float pdx = p[u].x - 0.5f, pdy = p[u].y - 0.5f;
                         unsigned bits[12];
 #pragma unroll
-                        for (int j = 0; j < ROWS; ++j) bits[j] = bin_bits((fny + (float)(j - H) - pdy) * P.iry * 16.f);
+                        for (int j = 0; j < ROWS; ++j) bits[j] = bin_bits((fny + (float)(j - H) - pdy) * iry16);
 #pragma unroll
                         for (int j = ROWS; j < 12; ++j) bits[j] = 0u;
                         // only the outermost rows can fall outside [ceil(pdy - r), floor(pdy + r)]
@@ -336,7 +341,7 @@ __global__ void __launch_bounds__(TW) splat_window_kernel(SplatParams P) {
                         const float4 a = pa[s];
                         const RB yb = pb[s];
                         const float pdx = a.w;
-                        unsigned ifx = bin_bits((fx - pdx) * P.irx * 16.f) & 0xFu;
+                        unsigned ifx = bin_bits((fx - pdx) * irx16) & 0xFu;
                         // Outermost columns: x must lie in [ceil(pdx - r), floor(pdx + r)].  Lanes hold sample
                         // s of neighbouring pixels, which for stratified streams sit in the same stratum and
                         // agree: vote and skip the sample for the whole warp when no lane needs it; a lane
