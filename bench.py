@@ -311,6 +311,8 @@ def main():
     }
 
     # ---- final assembly (once per render, not per step) ----------------------------------
+    # (a) baseline: resolve kernel, then one NCCL all_gather_into_tensor
+    pdist.assemble_film_rgb(film, 1.0)  # warm NCCL up
     barrier()
     a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a0.record(stream)
@@ -319,6 +321,22 @@ def main():
     barrier()
     assemble_ms = a0.elapsed_time(a1)
     assert tuple(frame.shape) == (H, W, 3)
+    # (b) fused: one kernel per rank resolves its rows and stores them into every rank's frame over NVLink
+    fx = pdist.FrameExchange(film)
+    fx.assemble(1.0)
+    barrier()
+    b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    b0.record(stream)
+    fx.launch(1.0)
+    b1.record(stream)
+    barrier()
+    fused = torch.tensor([b0.elapsed_time(b1)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(fused, op=dist.ReduceOp.MAX)
+    assemble_fused_ms = float(fused.item())
+    frame2 = fx.assemble(1.0)
+    assemble_identical = bool(torch.equal(frame2, frame))
+    fx.close()
 
     # ---- end to end through the public API with host buffers ------------------------------
     e2e = None
@@ -376,7 +394,9 @@ def main():
                        "cache": "inputs_exceed_l2" if n_local * 24 > 126e6 else "inputs_fit_l2",
                        "parallelism": f"rows x{world}", "tier": "extension (no reference parity): splat; merge+resolve are Tier 1"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
-            "clocks": clocks, "assemble_ms": assemble_ms,
+            "clocks": clocks,
+            "assemble": {"resolve_then_nccl_allgather_ms": assemble_ms, "fused_resolve_peer_store_ms": assemble_fused_ms,
+                         "frames_identical": assemble_identical, "bytes_per_rank": max(owned.area(), 0) * 12 * world},
             "percent_of_hbm_peak": 100.0 * achieved / peak,
         }
         if extras:

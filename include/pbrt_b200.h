@@ -70,6 +70,10 @@ int pbrt_b200_host_free(void *host);
 int pbrt_b200_memcpy_h2d(void *dev, const void *host, uint64_t bytes);
 int pbrt_b200_memcpy_d2h(void *host, const void *dev, uint64_t bytes);
 int pbrt_b200_memset(void *dev, int byte, uint64_t bytes);
+/* CUDA IPC for buffers from pbrt_b200_malloc: lets the ranks of one box map each other's frames */
+int pbrt_b200_ipc_export(void *dev, uint8_t handle[64]);
+int pbrt_b200_ipc_import(const uint8_t handle[64], void **dev_out);
+int pbrt_b200_ipc_close(void *dev);
 
 /* ------------------------------------------------------------------ filters (host) */
 enum { PBRT_FILTER_BOX = 0,       /* [T1] src/filters/box.rs:30-77 */
@@ -178,6 +182,14 @@ int pbrt_film_read_pixels(const PbrtFilm *film, float *out7, int dst_is_device);
  * xyzw = float4 {xyz, filter_weight_sum} per owned pixel, splat = 3 floats per owned pixel.
  */
 int pbrt_film_device_buffers(const PbrtFilm *film, void **xyzw, void **splat, int64_t *npixels);
+/*
+ * [T1]+[UTIL] the pixel loop of Film::write_image (film.rs:346-372) fused with the final assembly of a
+ * row-sharded film: resolves this film's rows and stores them straight into `nframes` full-frame rgb
+ * buffers — this rank's own and its peers' (mapped with pbrt_b200_ipc_import) — at the rows this film
+ * owns.  frames[i] holds 3 floats per pixel of cropped_pixel_bounds.  Every rank calling this once,
+ * followed by a barrier, is the all-gather: one kernel, peer stores over NVLink, no staging copy.
+ */
+int pbrt_film_resolve_rgb_to_frames(const PbrtFilm *film, float splat_scale, int32_t nframes, void *const *frames);
 /* [UTIL] sticky asynchronous error of the film's kernels (e.g. PBRT_E_NOT_PIXEL_MAJOR); clears it */
 int pbrt_film_check(PbrtFilm *film);
 

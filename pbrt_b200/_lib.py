@@ -54,6 +54,9 @@ PROTOTYPES = {
     "pbrt_b200_memcpy_h2d": (C.c_int, [_vp, _vp, C.c_uint64]),
     "pbrt_b200_memcpy_d2h": (C.c_int, [_vp, _vp, C.c_uint64]),
     "pbrt_b200_memset": (C.c_int, [_vp, C.c_int, C.c_uint64]),
+    "pbrt_b200_ipc_export": (C.c_int, [_vp, C.POINTER(C.c_uint8)]),
+    "pbrt_b200_ipc_import": (C.c_int, [C.POINTER(C.c_uint8), _vpp]),
+    "pbrt_b200_ipc_close": (C.c_int, [_vp]),
     "pbrt_filter_create": (C.c_int, [C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, _vpp]),
     "pbrt_box_filter_create_from_params": (C.c_int, [C.c_int, C.c_float, C.c_int, C.c_float, _vpp]),
     "pbrt_filter_destroy": (None, [_vp]),
@@ -84,6 +87,7 @@ PROTOTYPES = {
     "pbrt_film_get_pixel_xyz": (C.c_int, [_vp, C.c_int32, C.c_int32, _f32p]),
     "pbrt_film_read_pixels": (C.c_int, [_vp, _vp, C.c_int]),
     "pbrt_film_device_buffers": (C.c_int, [_vp, _vpp, _vpp, _i64p]),
+    "pbrt_film_resolve_rgb_to_frames": (C.c_int, [_vp, C.c_float, C.c_int32, _vpp]),
     "pbrt_film_check": (C.c_int, [_vp]),
     "pbrt_texture_constant_eval_f32": (C.c_int, [C.c_float, C.c_uint64, _vp, C.c_int]),
     "pbrt_texture_constant_eval_rgb": (C.c_int, [_f32p, C.c_uint64, _vp, C.c_int]),

@@ -177,6 +177,27 @@ extern "C" int pbrt_b200_memcpy_d2h(void *host, const void *dev, uint64_t bytes)
     PB_CUDA(cudaStreamSynchronize(ctx().stream));
     return PBRT_OK;
 }
+extern "C" int pbrt_b200_ipc_export(void *dev, uint8_t handle[64]) {
+    if (int rc = pb::ensure_ready()) return rc;
+    if (!dev || !handle) return fail(PBRT_E_INVALID, "null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    PB_CUDA(cudaIpcGetMemHandle(&h, dev));
+    memcpy(handle, &h, 64);
+    return PBRT_OK;
+}
+extern "C" int pbrt_b200_ipc_import(const uint8_t handle[64], void **out) {
+    if (int rc = pb::ensure_ready()) return rc;
+    if (!handle || !out) return fail(PBRT_E_INVALID, "null argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    PB_CUDA(cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess));
+    return PBRT_OK;
+}
+extern "C" int pbrt_b200_ipc_close(void *dev) {
+    if (dev) PB_CUDA(cudaIpcCloseMemHandle(dev));
+    return PBRT_OK;
+}
 extern "C" int pbrt_b200_memset(void *dev, int byte, uint64_t bytes) {
     if (int rc = pb::ensure_ready()) return rc;
     PB_CUDA(cudaMemsetAsync(dev, byte, bytes, ctx().stream));
@@ -735,6 +756,69 @@ extern "C" int pbrt_film_resolve_rgb(const PbrtFilm *f, float splat_scale, float
 }
 extern "C" int pbrt_film_resolve_rgb8(const PbrtFilm *f, float splat_scale, uint8_t *out, int dst_is_device) {
     return resolve_impl<true>(f, splat_scale, out, dst_is_device);
+}
+
+// resolve fused with the all-gather of a row-sharded film: every block stores its 256 resolved pixels
+// into each rank's full frame (local HBM for this rank, NVLink peer stores for the others)
+constexpr int MAX_FRAMES = 16;
+struct FrameList {
+    float *p[MAX_FRAMES];
+    int n;
+};
+
+__global__ void __launch_bounds__(RES_PIX) resolve_to_frames_kernel(const float4 *__restrict__ xyzw,
+                                                                    const float *__restrict__ splat, long long npix,
+                                                                    float splat_scale, float scale, FrameList frames,
+                                                                    long long frame_offset_px) {
+    __shared__ __align__(16) float s_in[RES_PIX * 3];
+    __shared__ __align__(16) float s_out[RES_PIX * 3];
+    const long long base = (long long)blockIdx.x * RES_PIX;
+    const int n = (int)min((long long)RES_PIX, npix - base);
+    const int tid = threadIdx.x;
+    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (tid < n) p = pb::ldg_stream(&xyzw[base + tid]);
+    if (n == RES_PIX) {
+        const float4 *src = reinterpret_cast<const float4 *>(splat + base * 3);
+        if (tid < RES_PIX * 3 / 4) reinterpret_cast<float4 *>(s_in)[tid] = pb::ldg_stream(&src[tid]);
+    } else {
+        for (int i = tid; i < n * 3; i += RES_PIX) s_in[i] = splat[base * 3 + i];
+    }
+    __syncthreads();
+    if (tid < n) {
+        float r, g, b;
+        resolve_pixel(p, s_in[3 * tid], s_in[3 * tid + 1], s_in[3 * tid + 2], splat_scale, scale, r, g, b);
+        s_out[3 * tid] = r; s_out[3 * tid + 1] = g; s_out[3 * tid + 2] = b;
+    }
+    __syncthreads();
+    const long long o = (frame_offset_px + base) * 3;  // float index in a frame; 16-byte aligned for full blocks
+    for (int f = 0; f < frames.n; ++f) {
+        float *dst = frames.p[f] + o;
+        if (n == RES_PIX && ((o & 3) == 0)) {
+            if (tid < RES_PIX * 3 / 4) reinterpret_cast<float4 *>(dst)[tid] = reinterpret_cast<float4 *>(s_out)[tid];
+        } else {
+            for (int i = tid; i < n * 3; i += RES_PIX) dst[i] = s_out[i];
+        }
+    }
+}
+
+extern "C" int pbrt_film_resolve_rgb_to_frames(const PbrtFilm *f, float splat_scale, int32_t nframes, void *const *frames) {
+    if (!f || !frames) return fail(PBRT_E_INVALID, "null argument");
+    if (nframes < 1 || nframes > MAX_FRAMES) return fail(PBRT_E_INVALID, "between 1 and %d frames", MAX_FRAMES);
+    if (f->npix == 0) return PBRT_OK;
+    if (f->owned.x0 != f->cropped.x0 || f->owned.x1 != f->cropped.x1)
+        return fail(PBRT_E_UNSUPPORTED, "row shards must span the full width");
+    FrameList fl;
+    fl.n = nframes;
+    for (int i = 0; i < nframes; ++i) {
+        if (!frames[i] || ((uintptr_t)frames[i] & 15)) return fail(PBRT_E_INVALID, "frame %d null or not 16-byte aligned", i);
+        fl.p[i] = (float *)frames[i];
+    }
+    const long long off = (long long)(f->owned.y0 - f->cropped.y0) * pb::bw(f->cropped);
+    int blocks = (int)((f->npix + RES_PIX - 1) / RES_PIX);
+    resolve_to_frames_kernel<<<blocks, RES_PIX, 0, ctx().stream>>>(f->d_xyzw, f->d_splat, (long long)f->npix, splat_scale,
+                                                                   f->scale, fl, off);
+    PB_LAUNCH_CHECK("resolve_to_frames_kernel");
+    return PBRT_OK;
 }
 
 extern "C" int pbrt_film_get_pixel_xyz(const PbrtFilm *f, int32_t x, int32_t y, float out[3]) {

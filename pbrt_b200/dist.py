@@ -78,3 +78,89 @@ def assemble_film_rgb(film, splat_scale: float = 1.0, group=None):
     local = torch.empty((h, w, 3), dtype=torch.float32, device="cuda")
     film.resolve_rgb(splat_scale, out=local)
     return allgather_rows(local, film.cropped_pixel_bounds, film.rank, film.nranks, group)
+
+
+class _DeviceArray:
+    """A device pointer dressed as __cuda_array_interface__ so torch can view it without a copy."""
+
+    def __init__(self, ptr: int, shape, typestr: str = "<f4"):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
+class FrameExchange:
+    """Final assembly of a row-sharded film as ONE kernel per rank over peer memory.
+
+    Every rank owns a full-frame rgb buffer; the buffers are exported through CUDA IPC and mapped by
+    every other rank once.  `assemble(film)` then runs `resolve_to_frames_kernel`: it resolves the
+    rank's rows (the write_image pixel loop) and stores them directly into all `nranks` frames —
+    local HBM for its own, NVLink peer stores for the others — so the all-gather needs no staging
+    buffer and no separate collective; a barrier afterwards makes every frame complete.
+    `assemble_film_rgb` (resolve, then NCCL all_gather_into_tensor) is the two-step baseline.
+    """
+
+    def __init__(self, film, group=None):
+        import ctypes as C
+
+        import torch
+        import torch.distributed as dist
+
+        from . import _lib
+        from .runtime import DeviceBuffer
+
+        self.film, self.group = film, group
+        self.rank, self.nranks = film.rank, film.nranks
+        c = film.cropped_pixel_bounds
+        self.w, self.h = c.p_max.x - c.p_min.x, c.p_max.y - c.p_min.y
+        self.frame = DeviceBuffer(max(self.w * self.h, 1) * 12)
+        self.frame.zero()
+        handle = (C.c_uint8 * 64)()
+        _lib.check(_lib.lib.pbrt_b200_ipc_export(C.c_void_p(self.frame.ptr), handle))
+        mine = torch.tensor(list(handle), dtype=torch.uint8, device="cuda")
+        allh = torch.empty((self.nranks, 64), dtype=torch.uint8, device="cuda")
+        if self.nranks > 1:
+            dist.all_gather_into_tensor(allh, mine, group=group)
+        else:
+            allh[0] = mine
+        allh = allh.cpu().numpy()
+        self.ptrs, self._opened = [], []
+        for r in range(self.nranks):
+            if r == self.rank:
+                self.ptrs.append(self.frame.ptr)
+                continue
+            hb = (C.c_uint8 * 64)(*[int(v) for v in allh[r]])
+            p = C.c_void_p()
+            _lib.check(_lib.lib.pbrt_b200_ipc_import(hb, C.byref(p)))
+            self.ptrs.append(p.value)
+            self._opened.append(p.value)
+        self._arr = (C.c_void_p * self.nranks)(*self.ptrs)
+
+    def assemble(self, splat_scale: float = 1.0):
+        """Returns the (H, W, 3) f32 frame (a view of this rank's buffer), complete on every rank."""
+        import ctypes as C
+
+        import torch
+        import torch.distributed as dist
+
+        from . import _lib
+
+        _lib.check(_lib.lib.pbrt_film_resolve_rgb_to_frames(self.film._h, float(splat_scale), self.nranks, self._arr))
+        torch.cuda.synchronize()
+        if self.nranks > 1:
+            dist.barrier(group=self.group)  # every peer's stores have landed in this rank's frame
+        return torch.as_tensor(_DeviceArray(self.frame.ptr, (self.h, self.w, 3)), device="cuda")
+
+    def launch(self, splat_scale: float = 1.0) -> None:
+        """Just the kernel (for timing on the device); `assemble` adds the synchronisation."""
+        from . import _lib
+
+        _lib.check(_lib.lib.pbrt_film_resolve_rgb_to_frames(self.film._h, float(splat_scale), self.nranks, self._arr))
+
+    def close(self) -> None:
+        import ctypes as C
+
+        from . import _lib
+
+        for p in self._opened:
+            _lib.lib.pbrt_b200_ipc_close(C.c_void_p(p))
+        self._opened = []
+        self.frame.free()
