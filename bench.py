@@ -160,7 +160,7 @@ class CpuArm:
         return time.perf_counter() - t0
 
 
-def run_reference(args, wl, rank, world):
+def run_reference(args, wl, rank, world, emit):
     """--impl reference: the reference's CPU implementation of the path on the host cores.
 
     The reference is Rust and cannot be compiled in this image (no rustc/cargo), so this arm times
@@ -191,7 +191,7 @@ def run_reference(args, wl, rank, world):
         "note": "the reference is Rust (no rustc here) and has no add_sample: this is oracle/pbrt_oracle.c, the C "
                 "restatement of its film path plus pbrt-v3's AddSample, on the host cores",
     }
-    print(json.dumps(out))
+    emit(out)
 
 
 # --------------------------------------------------------------------------------------- GPU arm
@@ -212,13 +212,24 @@ def main():
     ap.add_argument("--extras", action="store_true", help="also time merge / resolve / texture kernels")
     args = ap.parse_args()
 
+    # Rank 0 must print exactly one line on stdout.  Libraries (NCCL prints its version on first use)
+    # write to fd 1 too, so fd 1 is pointed at stderr for the whole run and the JSON line goes to a
+    # duplicate of the original stdout.
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+    def emit(obj):
+        real_stdout.write(json.dumps(obj) + "\n")
+        real_stdout.flush()
+
     wl = dict(WORKLOADS[args.workload])
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
 
     if args.impl == "reference":
-        run_reference(args, wl, rank, world)
+        run_reference(args, wl, rank, world, emit)
         return
 
     import numpy as np
@@ -401,7 +412,7 @@ def main():
         }
         if extras:
             out["extras"] = extras
-        print(json.dumps(out))
+        emit(out)
     if world > 1:
         dist.destroy_process_group()
 

@@ -17,7 +17,7 @@ CSRC = PKG / "csrc"
 LIB_DIR = PKG / "lib"
 LIB = LIB_DIR / "libpbrt_b200.so"
 SOURCES = ["film.cu", "splat.cu"]
-HEADERS = [CSRC / "common.cuh", ROOT / "include" / "pbrt_b200.h"]
+HEADERS = [CSRC / "common.cuh", CSRC / "to_byte_table.inc", ROOT / "include" / "pbrt_b200.h"]
 
 NVCC_FLAGS = [
     "-O3",

@@ -652,31 +652,22 @@ __device__ __forceinline__ void resolve_pixel(float4 p, float sx, float sy, floa
     r *= scale; g *= scale; b *= scale;
 }
 
-// src/lib.rs:93-99 + src/core/imageio.rs:66-68.  The byte only changes when 255*g + .5 crosses an
-// integer, so powf is evaluated in three tiers: the MUFU approximation (exp2(y*log2 x), a few 1e-6
-// relative) decides every value further than 4e-3 from a byte boundary; closer values are redone with
-// CUDA's accurate powf, and those still within 1e-3 through f64 pow, so that the byte agrees with a
-// correctly rounded f32 powf (what glibc's powf delivers for the CPU path).
-__device__ __forceinline__ unsigned char to_byte(float v) {
-    float g;
-    if (v <= 0.0031308f) {
-        g = 12.92f * v;
-    } else {
-        g = 1.055f * __powf(v, 1.f / 2.4f) - 0.055f;
-        float t = 255.f * g + 0.5f;
-        if (!(fabsf(t - rintf(t)) >= 4e-3f) && t > -1.f && t < 257.f) {
-            g = 1.055f * powf(v, 1.f / 2.4f) - 0.055f;
-            t = 255.f * g + 0.5f;
-            if (fabsf(t - rintf(t)) < 1e-3f) {
-                float p = (float)pow((double)v, (double)(1.f / 2.4f));
-                g = 1.055f * p - 0.055f;
-            }
-        }
-    }
-    float c = 255.f * g + 0.5f;
-    c = c < 0.f ? 0.f : (c > 255.f ? 255.f : c);  // src/lib.rs:115-126
-    if (!(c == c)) return 0;                      // `as u8` maps NaN to 0
-    return (unsigned char)c;
+// src/lib.rs:93-99 + src/core/imageio.rs:66-68: byte = clamp(255 * gamma_correct(v) + .5, 0, 255) as u8.
+// to_byte is monotone in v, so it is fully described by 255 thresholds: kToByteThreshold[k] is the smallest
+// f32 with to_byte >= k under a correctly rounded powf (tools/make_to_byte_table.py, no libm involved).
+// The kernel estimates the byte with the MUFU power approximation and corrects it against the
+// thresholds held in shared memory: exact for every input, no slow path, no f64.
+__device__ const unsigned kToByteThreshold[256] = {
+#include "to_byte_table.inc"
+};
+
+__device__ __forceinline__ unsigned char to_byte(float v, const float *thr) {
+    if (!(v >= thr[1])) return 0;  // below the first threshold, negative, or NaN (`as u8` maps NaN to 0)
+    const float g = v <= 0.0031308f ? 12.92f * v : 1.055f * __powf(v, 1.f / 2.4f) - 0.055f;
+    int k = (int)fminf(fmaxf(255.f * g + 0.5f, 1.f), 255.f);
+    while (k < 255 && v >= thr[k + 1]) ++k;
+    while (v < thr[k]) --k;  // thr[1] <= v, so this stops at k >= 1
+    return (unsigned char)k;
 }
 
 constexpr int RES_PIX = 256;  // pixels per block; 256*12 B = 3072 B, a multiple of 16
@@ -687,9 +678,11 @@ __global__ void __launch_bounds__(RES_PIX) resolve_kernel(const float4 *__restri
                                                           float splat_scale, float scale, void *__restrict__ out) {
     __shared__ __align__(16) float s_in[RES_PIX * 3];
     __shared__ __align__(16) float s_out[RES_PIX * 3];
+    __shared__ float s_thr[BYTES ? 256 : 1];
     const long long base = (long long)blockIdx.x * RES_PIX;
     const int n = (int)min((long long)RES_PIX, npix - base);
     const int tid = threadIdx.x;
+    if (BYTES) s_thr[tid] = __uint_as_float(kToByteThreshold[tid]);  // RES_PIX == 256 threads
     // 28 B / pixel in: float4 xyzw straight to a register, splat through shared memory
     float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
     if (tid < n) p = pb::ldg_stream(&xyzw[base + tid]);
@@ -705,7 +698,7 @@ __global__ void __launch_bounds__(RES_PIX) resolve_kernel(const float4 *__restri
         resolve_pixel(p, s_in[3 * tid], s_in[3 * tid + 1], s_in[3 * tid + 2], splat_scale, scale, r, g, b);
         if (BYTES) {
             unsigned char *o = reinterpret_cast<unsigned char *>(s_out);
-            o[3 * tid] = to_byte(r); o[3 * tid + 1] = to_byte(g); o[3 * tid + 2] = to_byte(b);
+            o[3 * tid] = to_byte(r, s_thr); o[3 * tid + 1] = to_byte(g, s_thr); o[3 * tid + 2] = to_byte(b, s_thr);
         } else {
             s_out[3 * tid] = r; s_out[3 * tid + 1] = g; s_out[3 * tid + 2] = b;
         }

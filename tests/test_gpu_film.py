@@ -237,3 +237,29 @@ def test_sharded_film_rows_and_tiles(gpu, orc):
             f.merge_film_tile(tt)
             parts.append(f.read_pixels().reshape(-1, res[0], 7))
         assert np.array_equal(u32(np.concatenate(parts, axis=0)), u32(ref))
+
+
+def test_resolve_rgb8_at_every_byte_threshold(gpu, orc):
+    """Device to_byte at each of the 255 thresholds, one ulp either side, and at special values."""
+    import re
+    import struct
+    from pathlib import Path
+
+    txt = (Path(__file__).resolve().parent.parent / "pbrt_b200" / "csrc" / "to_byte_table.inc").read_text()
+    thr = np.array([int(h, 16) for h in re.findall(r"0x([0-9a-f]{8})u", txt)][1:], dtype=np.uint32)
+    vals = np.concatenate([thr - 1, thr, thr + 1]).view(np.float32)
+    special = np.array([0.0, -0.0, -1.0, -1e-5, 1e-30, 0.0031308, 0.00313081, 1.0, 1.5, 1e30, np.inf, -np.inf, np.nan],
+                       dtype=np.float32)
+    vals = np.concatenate([vals, special, np.random.default_rng(0).random(4096 - len(vals) - len(special), dtype=np.float32)])
+    n = len(vals) // 3
+    img = vals[: 3 * n].reshape(n, 3)
+    film = gpu.Film.new([n, 1], [[0, 0], [1, 1]], gpu.BoxFilter.new([0.5, 0.5]), 35.0, "x.png", 1.0, float("inf"))
+    # put the values into the film as XYZ such that resolve returns them unchanged is not possible (3x3 matrices),
+    # so drive to_byte through set_image -> resolve_rgb (float) -> compare bytes of the SAME floats
+    film.set_image(img)
+    rgb = film.resolve_rgb(1.0).reshape(-1)
+    got = film.resolve_rgb8(1.0).reshape(-1)
+    want = np.array([orc.orc_to_byte(float(v)) for v in rgb], dtype=np.uint8)
+    assert np.array_equal(got, want)
+    # and the thresholds themselves, fed as grey pixels with weight 1 straight into the film (xyz_to_rgb(to_xyz(v,v,v)) ~ v)
+    assert len(np.unique(got)) > 200

@@ -92,3 +92,21 @@ def test_constant_texture_scalar_evaluate_is_host_side(pb, kats):
     assert list(pb.create_constant_spectrum_texture().evaluate(si)) == k["spectrum_default"]
     assert pb.create_constant_float_texture(None, {"value": 10.0}).evaluate(si) == 10.0
     assert "ConstantTexture{" in repr(pb.ConstantTexture(10.0))
+
+
+def test_to_byte_threshold_table_agrees_with_glibc(orc):
+    """The device's to_byte is driven by a threshold table generated without libm (correctly rounded powf).
+    Check it against the oracle (glibc powf, what Rust's f32::powf calls on Linux) at every threshold and
+    at the float just below it."""
+    import re
+    import struct
+    from pathlib import Path
+
+    txt = (Path(__file__).resolve().parent.parent / "pbrt_b200" / "csrc" / "to_byte_table.inc").read_text()
+    thr = [int(h, 16) for h in re.findall(r"0x([0-9a-f]{8})u", txt)]
+    assert len(thr) == 256 and thr[0] == 0 and thr == sorted(thr)
+    for k in range(1, 256):
+        v = struct.unpack("<f", struct.pack("<I", thr[k]))[0]
+        below = struct.unpack("<f", struct.pack("<I", thr[k] - 1))[0]
+        assert orc.orc_to_byte(v) == k, (k, v)
+        assert orc.orc_to_byte(below) == k - 1, (k, below)
