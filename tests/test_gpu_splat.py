@@ -116,6 +116,13 @@ def test_radii_covering_every_window_size(gpu, orc, radius):
     assert np.array_equal(u32(film.read_pixels()), u32(of.pixels()))
 
 
+@pytest.mark.parametrize("spp", [25, 64, 100, 256])
+def test_large_spp_uses_narrower_strips_exact(gpu, orc, spp):
+    """One sample row of a strip must fit in shared memory: 64 spp -> 64-column strips, 256 spp -> 32."""
+    film, of = run_pair(gpu, orc, "gaussian", (70, 12), [0, 0, 1, 1], (0, 0, 70, 12), spp, gpu.SPLAT_EXACT)
+    assert np.array_equal(u32(film.read_pixels()), u32(of.pixels()))
+
+
 @pytest.mark.parametrize("radius", [(8.0, 8.0), (2.0, 3.0), (0.3, 0.3), (5.0, 5.0)])
 def test_radii_served_by_the_generic_gather(gpu, orc, radius):
     film, of = run_pair(gpu, orc, "triangle", (48, 40), [0, 0, 1, 1], (0, 0, 48, 40), 4, gpu.SPLAT_EXACT, radius=radius)
