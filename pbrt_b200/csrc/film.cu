@@ -482,26 +482,45 @@ struct MergeIndex {
     const long long *tile_offset;
 };
 
+// One CTA per 16x16 cell: the cell's tile list (bounds, offsets) is the same for all 256 pixels, so it
+// is fetched into shared memory once and read back as broadcasts; the per-pixel work is then one
+// float4 film read, one float4 tile read per covering tile, one float4 film write.
+constexpr int MERGE_CHUNK = 32;
+
 __global__ void __launch_bounds__(256) merge_tiles_kernel(float4 *__restrict__ film, Bounds owned, MergeIndex ix,
                                                           const float4 *__restrict__ tiles) {
-    const int x = ix.box.x0 + blockIdx.x * 32 + (threadIdx.x & 31);
-    const int y = ix.box.y0 + blockIdx.y * 8 + (threadIdx.x >> 5);
-    if (x >= ix.box.x1 || y >= ix.box.y1) return;
-    const int cell = ((y - ix.box.y0) >> 4) * ix.cells_x + ((x - ix.box.x0) >> 4);
+    __shared__ int4 s_bounds[MERGE_CHUNK];
+    __shared__ long long s_offset[MERGE_CHUNK];
+    const int cell = blockIdx.y * ix.cells_x + blockIdx.x;
     const int beg = ix.cell_start[cell], end = ix.cell_start[cell + 1];
     if (beg == end) return;
+    const int x = ix.box.x0 + blockIdx.x * 16 + (threadIdx.x & 15);
+    const int y = ix.box.y0 + blockIdx.y * 16 + (threadIdx.x >> 4);
+    const bool in_box = x < ix.box.x1 && y < ix.box.y1;
     const size_t fo = (size_t)(y - owned.y0) * (owned.x1 - owned.x0) + (x - owned.x0);
-    float4 p = film[fo];
+    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (in_box) p = film[fo];
     bool touched = false;
-    for (int k = beg; k < end; ++k) {
-        const int t = ix.cell_tiles[k];
-        const int4 b = ix.tile_bounds[t];
-        if (x < b.x || x >= b.z || y < b.y || y >= b.w) continue;
-        float4 v = pb::ldg_stream(&tiles[ix.tile_offset[t] + (size_t)(y - b.y) * (b.z - b.x) + (x - b.x)]);
-        float X, Y, Z;
-        pb::rgb_to_xyz(v.x, v.y, v.z, X, Y, Z);
-        p.x += X; p.y += Y; p.z += Z; p.w += v.w;
-        touched = true;
+    for (int k0 = beg; k0 < end; k0 += MERGE_CHUNK) {
+        const int n = min(MERGE_CHUNK, end - k0);
+        __syncthreads();
+        if ((int)threadIdx.x < n) {
+            const int t = ix.cell_tiles[k0 + threadIdx.x];
+            s_bounds[threadIdx.x] = ix.tile_bounds[t];
+            s_offset[threadIdx.x] = ix.tile_offset[t];
+        }
+        __syncthreads();
+        if (in_box) {
+            for (int k = 0; k < n; ++k) {  // ascending tile index: the order sequential merge_film_tile calls would use
+                const int4 b = s_bounds[k];
+                if (x < b.x || x >= b.z || y < b.y || y >= b.w) continue;
+                const float4 v = pb::ldg_stream(&tiles[s_offset[k] + (size_t)(y - b.y) * (b.z - b.x) + (x - b.x)]);
+                float X, Y, Z;
+                pb::rgb_to_xyz(v.x, v.y, v.z, X, Y, Z);
+                p.x += X; p.y += Y; p.z += Z; p.w += v.w;
+                touched = true;
+            }
+        }
     }
     if (touched) film[fo] = p;
 }
@@ -627,7 +646,7 @@ extern "C" int pbrt_film_merge_tiles(PbrtFilm *f, int32_t ntiles, const int32_t 
     ix.cell_tiles = (const int *)((char *)d_blob + b1);
     ix.tile_bounds = (const int4 *)((char *)d_blob + b2);
     ix.tile_offset = (const long long *)((char *)d_blob + b3);
-    dim3 grid((pb::bw(box) + 31) / 32, (pb::bh(box) + 7) / 8);
+    dim3 grid(cx, (pb::bh(box) + 15) / 16);  // one CTA per 16x16 cell of the index
     merge_tiles_kernel<<<grid, 256, 0, ctx().stream>>>(f->d_xyzw, f->owned, ix, d_tiles);
     PB_LAUNCH_CHECK("merge_tiles_kernel");
     return PBRT_OK;
@@ -664,9 +683,11 @@ __device__ const unsigned kToByteThreshold[256] = {
 __device__ __forceinline__ unsigned char to_byte(float v, const float *thr) {
     if (!(v >= thr[1])) return 0;  // below the first threshold, negative, or NaN (`as u8` maps NaN to 0)
     const float g = v <= 0.0031308f ? 12.92f * v : 1.055f * __powf(v, 1.f / 2.4f) - 0.055f;
+    // the MUFU estimate of 255*g + .5 is within 1e-3 of the exactly rounded value, so its floor is off by
+    // at most one: one step up and one step down against the thresholds settle it without a branch
     int k = (int)fminf(fmaxf(255.f * g + 0.5f, 1.f), 255.f);
-    while (k < 255 && v >= thr[k + 1]) ++k;
-    while (v < thr[k]) --k;  // thr[1] <= v, so this stops at k >= 1
+    k += (k < 255) & (v >= thr[min(k + 1, 255)]);
+    k -= v < thr[k];  // thr[1] <= v, so k stays >= 1
     return (unsigned char)k;
 }
 
