@@ -48,6 +48,10 @@ WORKLOADS = {
                label="3840x2160 film, Mitchell r=2, one 16-spp pass of the 64 spp (BASELINE configs[2])"),
     "c5": dict(res=(7680, 4320), spp=16, filter="lanczos", radius=(4.0, 4.0), p0=3.0, p1=0.0,
                label="7680x4320 film, Lanczos-sinc r=4, one 16-spp pass of the 256 spp (BASELINE configs[4])"),
+    "c2_spp8": dict(res=(1920, 1080), spp=8, filter="gaussian", radius=(2.0, 2.0), p0=2.0, p1=0.0,
+                    label="1920x1080 film, 8 spp per pass, Gaussian r=2 (occupancy experiment, not a BASELINE config)"),
+    "c2_spp4": dict(res=(1920, 1080), spp=4, filter="gaussian", radius=(2.0, 2.0), p0=2.0, p1=0.0,
+                    label="1920x1080 film, 4 spp per pass, Gaussian r=2 (occupancy experiment, not a BASELINE config)"),
     "c1": dict(res=(64, 64), spp=4, filter="gaussian", radius=(2.0, 2.0), p0=2.0, p1=0.0,
                label="64x64 film, 4 spp (BASELINE configs[0])"),
 }
@@ -209,7 +213,8 @@ def main():
     ap.add_argument("--ref-band-rows", type=int, default=1080, help="band of the film the --impl reference arm runs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--extras", action="store_true", help="also time merge / resolve / texture kernels")
+    ap.add_argument("--extras", action="store_true", help="(default at N=1) also time the Tier-1 merge / resolve / texture kernels")
+    ap.add_argument("--no-extras", action="store_true")
     args = ap.parse_args()
 
     # Rank 0 must print exactly one line on stdout.  Libraries (NCCL prints its version on first use)
@@ -381,8 +386,11 @@ def main():
 
     # ---- secondary kernels (Tier 1: merge / resolve / constant texture) -------------------
     extras = None
-    if args.extras and rank == 0:
-        extras = time_extras(pb, synth, film, torch, stream, peak)
+    if rank == 0 and not args.no_extras and (args.extras or world == 1):
+        try:
+            extras = time_extras(pb, synth, film, torch, stream, peak)
+        except Exception as e:  # the headline line must still be printed
+            extras = {"error": f"{type(e).__name__}: {e}"}
 
     # ---- CPU baseline beside it: rank 0, N = 1 only --------------------------------------
     cpu = None
