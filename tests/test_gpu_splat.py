@@ -271,3 +271,25 @@ def test_full_size_c2_properties(gpu, orc):
     f3 = gpu.Film.new(res, [[0, 0], [1, 1]], filt, 35.0, "x.pfm", 1.0, float("inf"))
     f3.add_samples_tile([[0, 0], list(res)], spp, xy_d, rgbw_d, gpu.SPLAT_FMA)
     assert rel_err(f3.read_pixels()[:, :4], films[0][:, :4]) <= REL_TOL
+
+
+@pytest.mark.parametrize("name", list(oracle.FILTERS))
+def test_c1_matches_committed_golden(gpu, name):
+    """CUDA path against the committed fixture alone (no oracle call): device sample generator -> splat -> resolve."""
+    import hashlib
+    import json
+    from pathlib import Path
+
+    from pbrt_b200 import synth
+
+    g = json.loads((Path(__file__).resolve().parent / "golden" / "ext_c1_golden.json").read_text())["filters"][name]
+    filt, kind, rad, p0, p1 = make_filter(gpu, name)
+    assert hashlib.sha256(gpu.filter_table(filt).tobytes()).hexdigest() == g["table_sha256"]
+    film = gpu.Film.new((64, 64), [[0, 0], [1, 1]], filt, 35.0, "x.pfm", 1.0, float("inf"))
+    xy, rgbw, n = synth.samples((0, 0, 64, 64), 4, seed=1)
+    film.add_samples_tile((0, 0, 64, 64), 4, xy, rgbw, gpu.SPLAT_EXACT)
+    film.check()
+    px = film.read_pixels()
+    assert [int(v) for v in px[32 * 64 + 32, :4].view(np.uint32)] == g["pixel_32_32_xyzw_bits"]
+    assert hashlib.sha256(np.ascontiguousarray(px[:, :4]).tobytes()).hexdigest() == g["pixels_sha256"]
+    assert hashlib.sha256(film.resolve_rgb(1.0).tobytes()).hexdigest() == g["rgb_sha256"]

@@ -280,3 +280,22 @@ def test_ext_synth_samples_layout(orc):
     # stratified: sample s of a pixel lies in cell (s % 2, s // 2)
     cell_x = np.floor((xy[:, 0] - px) * 2).astype(int)
     assert (cell_x == np.tile([0, 1, 0, 1], 12)).all()
+
+
+def test_ext_c1_matches_committed_golden(orc):
+    """The oracle reproduces tests/golden/ext_c1_golden.json (made by tests/golden/make_ext_golden.py)."""
+    import hashlib
+    import json
+    from pathlib import Path
+
+    g = json.loads((Path(__file__).resolve().parent / "golden" / "ext_c1_golden.json").read_text())
+    for name, want in g["filters"].items():
+        kind, rad, p0, p1 = oracle.FILTERS[name]
+        table = oracle.filter_table(orc, kind, rad, p0, p1)
+        assert hashlib.sha256(table.tobytes()).hexdigest() == want["table_sha256"], name
+        film = OracleFilm(orc, (64, 64), [0, 0, 1, 1], rad, table)
+        xy, rgbw = oracle.synth_samples(orc, (0, 0, 64, 64), 4, 1)
+        film.add_samples_pass((0, 0, 64, 64), 4, xy, rgbw, threads=3)
+        px = film.pixels()
+        assert hashlib.sha256(np.ascontiguousarray(px[:, :4]).tobytes()).hexdigest() == want["pixels_sha256"], name
+        assert hashlib.sha256(film.write_image_rgb(1.0).tobytes()).hexdigest() == want["rgb_sha256"], name
