@@ -26,7 +26,7 @@ class PbrtError(RuntimeError):
 
 if not LIB_PATH.exists():
     raise ImportError(
-        f"{LIB_PATH} not found: build it with `python -m pbrt_b200.build` "
+        f"{LIB_PATH} not found: build it with `python build_native.py` "
         "(libpbrt_b200 is CUDA-only; there is no CPU fallback)"
     )
 

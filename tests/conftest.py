@@ -28,9 +28,9 @@ def kats():
 @pytest.fixture(scope="session")
 def pb():
     """The product package, with the CUDA library built in-tree."""
-    from pbrt_b200 import build as _build
+    import build_native
 
-    _build.build()
+    build_native.build()
     import pbrt_b200
 
     return pbrt_b200

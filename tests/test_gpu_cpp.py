@@ -10,9 +10,12 @@ BIN = ROOT / "tests" / "cpp" / "build" / "test_film"
 
 
 def build_cpp_test() -> Path:
-    from pbrt_b200 import build as _b
+    import sys
 
-    lib = _b.build()
+    sys.path.insert(0, str(ROOT))
+    import build_native
+
+    lib = build_native.build()
     src = ROOT / "tests" / "cpp" / "test_film.cpp"
     deps = [src, ROOT / "include" / "pbrt_b200.hpp", ROOT / "include" / "pbrt_b200.h", lib]
     if not BIN.exists() or any(d.stat().st_mtime > BIN.stat().st_mtime for d in deps):
