@@ -388,7 +388,7 @@ def main():
     extras = None
     if rank == 0 and not args.no_extras and (args.extras or world == 1):
         try:
-            extras = time_extras(pb, synth, film, torch, stream, peak)
+            extras = time_extras(pb, synth, film, torch, stream, peak, xy_d, rgbw_d, spp)
         except Exception as e:  # the headline line must still be printed
             extras = {"error": f"{type(e).__name__}: {e}"}
 
@@ -425,7 +425,7 @@ def main():
         dist.destroy_process_group()
 
 
-def time_extras(pb, synth, film, torch, stream, peak):
+def time_extras(pb, synth, film, torch, stream, peak, xy_main=None, rgbw_main=None, spp_main=16):
     """Tier-1 kernels (reference-backed): merge_film_tile (48 B/tile px), write_image's resolve (40 B/px),
     ConstantTexture lookups (4 / 12 B).  Run on a 7680x4320 film so that every working set (>= 531 MB)
     exceeds the 126 MB L2 and the numbers are HBM numbers."""
@@ -480,6 +480,32 @@ def time_extras(pb, synth, film, torch, stream, peak):
     out["resolve_rgb8"] = entry(npx, 31, ms, "px_per_s", note="fused gamma_correct + to_byte (imageio.rs:66-68)")
     del rgb8
     big.close()
+    # a16 the way a renderer feeds it: 16x16-sample tiles (pbrt's tile size), each accumulated separately and
+    # merged in order — one call, two launches
+    try:
+        from pbrt_b200.dist import _DeviceArray
+
+        W, H = film.cropped_pixel_bounds.p_max.x, film.cropped_pixel_bounds.p_max.y
+        spp = spp_main
+        ys, xs = torch.meshgrid(torch.arange(H, device="cuda"), torch.arange(W, device="cuda"), indexing="ij")
+        ty, tx = ys // 16, xs // 16
+        tiles_x = (W + 15) // 16
+        tile_id = (ty * tiles_x + tx).reshape(-1)
+        order = torch.argsort(tile_id, stable=True)          # pixels grouped by tile, row-major inside a tile
+        sidx = (order[:, None] * spp + torch.arange(spp, device="cuda")[None, :]).reshape(-1)
+        n_s = W * H * spp
+        xy_t = torch.as_tensor(_DeviceArray(xy_main.ptr, (n_s, 2)), device="cuda")[sidx].contiguous()
+        rgbw_t = torch.as_tensor(_DeviceArray(rgbw_main.ptr, (n_s, 4)), device="cuda")[sidx].contiguous()
+        sbs = [(x, y, min(x + 16, W), min(y + 16, H)) for y in range(0, H, 16) for x in range(0, W, 16)]
+        small = pb.Film.new([W, H], [[0, 0], [1, 1]], film.filter, 35.0, "extras_tiles.pfm", 1.0, float("inf"))
+        ms = timed(lambda: small.add_samples_tiles(sbs, spp, xy_t, rgbw_t), reps=5)
+        small.check()
+        out["splat_tiles_16x16"] = {"samples_per_s": n_s / (ms * 1e-3), "ms": ms, "tiles": len(sbs),
+                                    "note": "whole call: host tile descriptors + upload, splat into per-tile buffers, ordered merge"}
+        small.close()
+        del xy_t, rgbw_t, sidx, order
+    except Exception as e:
+        out["splat_tiles_16x16"] = {"error": f"{type(e).__name__}: {e}"}
     # a14: 1e8 lookups
     n = 100_000_000
     t1 = torch.empty(n, dtype=torch.float32, device="cuda")

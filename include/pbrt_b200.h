@@ -156,6 +156,17 @@ enum { PBRT_SPLAT_EXACT = 0,   /* gather, mul then add: bit-identical to the CPU
 int pbrt_film_add_samples_tile(PbrtFilm *film, const int32_t sample_bounds[4], int32_t spp, const float *xy,
                                const float *rgbw, int src_is_device, int mode);
 /*
+ * [T2] the same for `ntiles` tiles at once, the way a renderer works (pbrt renders 16x16-pixel tiles):
+ * tile i has sample bounds sample_bounds[4i..4i+3] and its pixel-major samples start at sample
+ * sample_offsets[i] of xy / rgbw.  Equivalent to add_samples_tile for i = 0 .. ntiles-1 in order: every
+ * tile is accumulated on its own (FilmTile semantics), then the tiles are merged in tile order, so
+ * pixels in overlapping tile borders receive their contributions exactly as sequential calls would give.
+ * Two launches in total (splat into per-tile RGBW buffers, ordered merge) instead of 2 per tile.
+ */
+int pbrt_film_add_samples_tiles(PbrtFilm *film, int32_t ntiles, const int32_t *sample_bounds,
+                                const int64_t *sample_offsets, int32_t spp, const float *xy, const float *rgbw,
+                                int64_t total_samples, int src_is_device, int mode);
+/*
  * [T2] the same for samples in arbitrary order and position (no pixel-major contract):
  * scatter with global atomics into a scratch tile, then merge.  Order not deterministic.
  */

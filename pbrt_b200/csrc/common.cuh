@@ -111,6 +111,8 @@ struct PbrtFilm {
     int idx_cells_x;
     size_t idx_off[4];
     int64_t idx_need;        // pixels the batch's rgbw buffer must hold
+    void *d_tile_desc;       // add_samples_tiles: SplatTile array (grow-only)
+    size_t tile_desc_bytes;
 };
 
 namespace pb {
@@ -142,7 +144,16 @@ int stage_in(PbrtFilm *f, int slot, const void *host, size_t bytes, void **dev_o
         if (_e != cudaSuccess) return pb::cuda_fail(_e, name);    \
     } while (0)
 
+// one tile of a batched splat (pbrt_film_add_samples_tiles)
+struct SplatTile {
+    Bounds sb, tb;            // sample bounds; tile pixel bounds = get_film_tile(sb)
+    long long sample_offset;  // first sample of the tile in xy / rgbw
+    long long pixel_offset;   // first pixel of the tile in the RGBW scratch buffer
+};
+
 // kernels implemented in splat.cu
+int launch_splat_tiles(PbrtFilm *f, int ntiles, const SplatTile *d_tiles, int max_w, int max_h, int spp, const float2 *xy,
+                       const float4 *rgbw, float4 *tile_out, int mode);
 int launch_splat_tile(PbrtFilm *f, const Bounds &sb, const Bounds &tb, int spp, const float2 *xy, const float4 *rgbw,
                       int mode);
 

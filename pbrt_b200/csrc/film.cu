@@ -376,6 +376,7 @@ extern "C" int pbrt_film_destroy(PbrtFilm *f) {
     cudaFree(f->d_stage[1]);
     cudaFree(f->d_scratch_tile);
     cudaFree(f->d_idx);
+    cudaFree(f->d_tile_desc);
     free(f->idx_bounds);
     free(f->idx_offsets);
     cudaGetLastError();
@@ -1073,6 +1074,79 @@ extern "C" int pbrt_film_add_samples_tile(PbrtFilm *f, const int32_t sbv[4], int
         return fail(PBRT_E_INVALID, "device sample streams must be 8- (xy) and 16-byte (rgbw) aligned");
     }
     return pb::launch_splat_tile(f, sb, tb, spp, d_xy, d_rgbw, mode);
+}
+
+// [T2] many tiles per call: splat every tile into its own RGBW buffer, then the ordered batched merge
+extern "C" int pbrt_film_add_samples_tiles(PbrtFilm *f, int32_t ntiles, const int32_t *sbs, const int64_t *sample_offsets,
+                                           int32_t spp, const float *xy, const float *rgbw, int64_t total_samples,
+                                           int src_is_device, int mode) {
+    if (!f) return fail(PBRT_E_INVALID, "null film");
+    if (ntiles <= 0) return PBRT_OK;
+    if (!sbs || !sample_offsets || !xy || !rgbw) return fail(PBRT_E_INVALID, "null argument");
+    if (spp < 1) return fail(PBRT_E_INVALID, "spp must be >= 1");
+    if (mode != PBRT_SPLAT_EXACT && mode != PBRT_SPLAT_FMA) return fail(PBRT_E_INVALID, "batched tiles support PBRT_SPLAT_EXACT and PBRT_SPLAT_FMA");
+    std::vector<pb::SplatTile> desc(ntiles);
+    std::vector<int32_t> tbs((size_t)ntiles * 4);
+    std::vector<int64_t> poffs(ntiles);
+    int64_t total_px = 0;
+    int max_w = 0, max_h = 0;
+    for (int i = 0; i < ntiles; ++i) {
+        Bounds sb{sbs[4 * i], sbs[4 * i + 1], sbs[4 * i + 2], sbs[4 * i + 3]};
+        Bounds tb;
+        if (int rc = tile_bounds_impl(f, &sbs[4 * i], f->owned, &tb)) return rc;
+        const bool empty = sb.x1 <= sb.x0 || sb.y1 <= sb.y0 || tb.x1 <= tb.x0 || tb.y1 <= tb.y0;
+        if (empty) tb = Bounds{0, 0, 0, 0};  // a tile without samples merges zeros: nothing to do
+        const int64_t ns = empty ? 0 : (int64_t)pb::bw(sb) * pb::bh(sb) * spp;
+        if (sample_offsets[i] < 0 || sample_offsets[i] + ns > total_samples)
+            return fail(PBRT_E_INVALID, "tile %d: samples outside the stream", i);
+        desc[i].sb = sb; desc[i].tb = tb;
+        desc[i].sample_offset = sample_offsets[i];
+        desc[i].pixel_offset = total_px;
+        poffs[i] = total_px;
+        tbs[4 * i] = tb.x0; tbs[4 * i + 1] = tb.y0; tbs[4 * i + 2] = tb.x1; tbs[4 * i + 3] = tb.y1;
+        total_px += (int64_t)pb::bw(tb) * pb::bh(tb);
+        max_w = std::max(max_w, pb::bw(tb)); max_h = std::max(max_h, pb::bh(tb));
+    }
+    if (total_px == 0) return PBRT_OK;
+    const float2 *d_xy = (const float2 *)xy;
+    const float4 *d_rgbw = (const float4 *)rgbw;
+    if (!src_is_device) {
+        void *a, *b;
+        if (int rc = pb::stage_in(f, 0, xy, (size_t)total_samples * sizeof(float2), &a)) return rc;
+        if (int rc = pb::stage_in(f, 1, rgbw, (size_t)total_samples * sizeof(float4), &b)) return rc;
+        d_xy = (const float2 *)a; d_rgbw = (const float4 *)b;
+    }
+    if ((size_t)total_px > f->scratch_tile_px) {
+        cudaFree(f->d_scratch_tile);
+        f->d_scratch_tile = nullptr;
+        f->scratch_tile_px = 0;
+        PB_CUDA(cudaMalloc(&f->d_scratch_tile, (size_t)total_px * sizeof(float4)));
+        f->scratch_tile_px = (size_t)total_px;
+    }
+    const size_t dbytes = desc.size() * sizeof(pb::SplatTile);
+    if (dbytes > f->tile_desc_bytes) {
+        cudaFree(f->d_tile_desc);
+        f->d_tile_desc = nullptr;
+        f->tile_desc_bytes = 0;
+        PB_CUDA(cudaMalloc(&f->d_tile_desc, dbytes + 256));
+        f->tile_desc_bytes = dbytes + 256;
+    }
+    PB_CUDA(cudaMemcpyAsync(f->d_tile_desc, desc.data(), dbytes, cudaMemcpyHostToDevice, ctx().stream));
+    PB_CUDA(cudaStreamSynchronize(ctx().stream));  // desc is a local
+    int rc = pb::launch_splat_tiles(f, ntiles, (const pb::SplatTile *)f->d_tile_desc, max_w, max_h, spp, d_xy, d_rgbw,
+                                    f->d_scratch_tile, mode);
+    if (rc < 0) {
+        // radius outside the window kernel's range: one tile at a time, which is the same thing by definition
+        for (int i = 0; i < ntiles; ++i) {
+            if (desc[i].tb.x1 <= desc[i].tb.x0) continue;
+            if (int r2 = pb::launch_splat_tile(f, desc[i].sb, desc[i].tb, spp, d_xy + desc[i].sample_offset,
+                                               d_rgbw + desc[i].sample_offset, mode))
+                return r2;
+        }
+        return PBRT_OK;
+    }
+    if (rc != PBRT_OK) return rc;
+    return pbrt_film_merge_tiles(f, ntiles, tbs.data(), poffs.data(), (const float *)f->d_scratch_tile, total_px, 1);
 }
 
 // ===================================================================== kernels: textures, LUT, synthetic inputs

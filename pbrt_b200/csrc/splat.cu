@@ -48,7 +48,12 @@ struct SplatParams {
     int *err;
     int rows_per_cta;
     unsigned negzero_bits;  // 0x80000000, passed at run time so ptxas cannot constant-fold it (see accumulate())
+    // batched mode (pbrt_film_add_samples_tiles): blockIdx.z selects a tile; its bounds and streams replace
+    // sb / tb / xy / rgbw, and finished pixels go to the tile's own RGBW buffer instead of the film
+    const SplatTile *tiles;
+    float4 *tile_out;
 };
+
 
 // ---- pieces shared by all variants -------------------------------------------------------
 
@@ -228,6 +233,17 @@ __global__ void __launch_bounds__(TW) splat_window_kernel(SplatParams P) {
     RB *s_b = reinterpret_cast<RB *>(smem + WIN_TABLE_BYTES + (size_t)NPX * pitch * 16);
 
     const int tid = threadIdx.x;
+    float4 *tile_out = nullptr;
+    if (P.tiles) {  // batched: this CTA works on tile blockIdx.z (uniform across the grid's z slice)
+        const SplatTile t = P.tiles[blockIdx.z];
+        P.sb = t.sb;
+        P.tb = t.tb;
+        P.xy += t.sample_offset;
+        P.rgbw += t.sample_offset;
+        tile_out = P.tile_out + t.pixel_offset;
+        if (P.tb.x1 <= P.tb.x0 || P.tb.y1 <= P.tb.y0 || P.sb.x1 <= P.sb.x0 || P.sb.y1 <= P.sb.y0) return;
+        if (P.tb.x0 + (int)blockIdx.x * TW >= P.tb.x1) return;  // the grid is sized for the widest tile
+    }
     for (int i = tid; i < 17 * 17; i += TW) {
         const int ty = i / 17, tx = i - ty * 17;
         const float w = (ty < 16 && tx < 16) ? P.table[ty * 16 + tx] : 0.f;
@@ -378,7 +394,10 @@ __global__ void __launch_bounds__(TW) splat_window_kernel(SplatParams P) {
             float r, g, b, w;
             unpack2(acc_rg[0], r, g);
             unpack2(acc_bw[0], b, w);
-            flush_pixel(P.film, P.owned, x, yo, r, g, b, w);
+            if (tile_out)  // FilmTilePixel {contrib_sum, filter_weight_sum} of this tile (film.rs:39-42)
+                tile_out[(size_t)(yo - P.tb.y0) * (P.tb.x1 - P.tb.x0) + (x - P.tb.x0)] = make_float4(r, g, b, w);
+            else
+                flush_pixel(P.film, P.owned, x, yo, r, g, b, w);
         }
 #pragma unroll
         for (int j = 0; j + 1 < ROWS; ++j) { acc_rg[j] = acc_rg[j + 1]; acc_bw[j] = acc_bw[j + 1]; }
@@ -516,6 +535,62 @@ static int pick_window(const SplatParams &P, int h) {
     return -1;
 }
 
+// ---- batched tiles ---------------------------------------------------------------------------
+
+template <int H, bool FMA>
+static int launch_window_batched(const SplatParams &P0, int ntiles, int max_w, int max_h) {
+    constexpr int TW = 32;  // renderer tiles are small (16x16 samples -> 20x20 pixels at r = 2)
+    SplatParams P = P0;
+    const size_t smem = WinSmem<H, TW>::bytes(P.spp);
+    if (smem > 227 * 1024) return -1;
+    static bool attr_set = false;
+    if (!attr_set) {
+        PB_CUDA(cudaFuncSetAttribute(splat_window_kernel<H, TW, FMA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     227 * 1024));
+        attr_set = true;
+    }
+    P.rows_per_cta = std::max(max_h, 1);  // one CTA column strip walks the whole tile height
+    for (int z0 = 0; z0 < ntiles; z0 += 65535) {
+        const int nz = std::min(65535, ntiles - z0);
+        SplatParams Q = P;
+        Q.tiles = P.tiles + z0;
+        dim3 grid((max_w + TW - 1) / TW, 1, nz);
+        splat_window_kernel<H, TW, FMA><<<grid, TW, smem, ctx().stream>>>(Q);
+        PB_LAUNCH_CHECK("splat_window_kernel(batched)");
+    }
+    return PBRT_OK;
+}
+
+// tiles: device array of ntiles SplatTile; tile_out: device RGBW scratch the tiles' pixels go to
+int launch_splat_tiles(PbrtFilm *f, int ntiles, const SplatTile *d_tiles, int max_w, int max_h, int spp, const float2 *xy,
+                       const float4 *rgbw, float4 *tile_out, int mode) {
+    SplatParams P;
+    P.sb = P.tb = Bounds{0, 0, 0, 0};
+    P.owned = f->owned;
+    P.spp = spp;
+    P.rx = f->radius[0]; P.ry = f->radius[1];
+    P.irx = f->inv_radius[0]; P.iry = f->inv_radius[1];
+    P.max_lum = f->max_lum;
+    P.xy = xy; P.rgbw = rgbw;
+    P.table = f->d_table;
+    P.film = f->d_xyzw;
+    P.err = f->d_err;
+    P.rows_per_cta = 0;
+    P.negzero_bits = 0x80000000u;
+    P.tiles = d_tiles;
+    P.tile_out = tile_out;
+    const int hx = (int)floorf(P.rx + 0.5f), hy = (int)floorf(P.ry + 0.5f);
+    if (hx != hy || hx < 1 || hx > 4) return -1;  // caller falls back to one launch per tile
+    const bool fma = mode == PBRT_SPLAT_FMA;
+    switch (hx) {
+    case 1: return fma ? launch_window_batched<1, true>(P, ntiles, max_w, max_h) : launch_window_batched<1, false>(P, ntiles, max_w, max_h);
+    case 2: return fma ? launch_window_batched<2, true>(P, ntiles, max_w, max_h) : launch_window_batched<2, false>(P, ntiles, max_w, max_h);
+    case 3: return fma ? launch_window_batched<3, true>(P, ntiles, max_w, max_h) : launch_window_batched<3, false>(P, ntiles, max_w, max_h);
+    case 4: return fma ? launch_window_batched<4, true>(P, ntiles, max_w, max_h) : launch_window_batched<4, false>(P, ntiles, max_w, max_h);
+    }
+    return -1;
+}
+
 static int g_force_generic = 0;
 
 int launch_splat_tile(PbrtFilm *f, const Bounds &sb, const Bounds &tb, int spp, const float2 *xy, const float4 *rgbw,
@@ -532,6 +607,8 @@ int launch_splat_tile(PbrtFilm *f, const Bounds &sb, const Bounds &tb, int spp, 
     P.err = f->d_err;
     P.rows_per_cta = 0;
     P.negzero_bits = 0x80000000u;
+    P.tiles = nullptr;
+    P.tile_out = nullptr;
     if (!(P.rx > 0.f) || !(P.ry > 0.f) || P.rx > 1024.f || P.ry > 1024.f)
         return fail(PBRT_E_UNSUPPORTED, "filter radius (%g, %g) outside (0, 1024]", P.rx, P.ry);
     // a sample in nominal pixel n reaches pixels n - h .. n + h, h = floor(r + .5)

@@ -241,6 +241,27 @@ class Film:
             raise ValueError("xy and rgbw must both be host or both be device buffers")
         _lib.check(_lib.lib.pbrt_film_add_samples_tile(self._h, _lib.i32x4(sb.as4()), int(spp), pxy, prgbw, dev_a, int(mode)))
 
+    def add_samples_tiles(self, sample_bounds, spp: int, xy, rgbw, sample_offsets=None, mode: int = SPLAT_EXACT) -> None:
+        """Many tiles in one call: tile i has sample bounds `sample_bounds[i]` (x0, y0, x1, y1) and its pixel-major
+        samples start at `sample_offsets[i]` (default: tiles packed back to back).  Same result as calling
+        add_samples_tile for each tile in order."""
+        sbs = np.ascontiguousarray([Bounds2i.of(b).as4() for b in sample_bounds], dtype=np.int32)
+        counts = np.array([max(b[2] - b[0], 0) * max(b[3] - b[1], 0) * spp for b in sbs], dtype=np.int64)
+        if sample_offsets is None:
+            sample_offsets = np.concatenate([[0], np.cumsum(counts)[:-1]])
+        offs = np.ascontiguousarray(sample_offsets, dtype=np.int64)
+        pxy, dev_a, k1 = as_pointer(xy)
+        prgbw, dev_b, k2 = as_pointer(rgbw)
+        if dev_a != dev_b:
+            raise ValueError("xy and rgbw must both be host or both be device buffers")
+        total = int((np.asarray(k1).size // 2) if not dev_a else (k1.nbytes // 8))
+        _lib.check(
+            _lib.lib.pbrt_film_add_samples_tiles(
+                self._h, len(sbs), sbs.ctypes.data_as(C.POINTER(C.c_int32)), offs.ctypes.data_as(C.POINTER(C.c_int64)),
+                int(spp), pxy, prgbw, total, dev_a, int(mode),
+            )
+        )
+
     def add_samples(self, sample_bounds, xy, rgbw) -> None:
         """Samples in any order / position (global-atomic scatter; order of additions not fixed)."""
         sb = Bounds2i.of(sample_bounds)

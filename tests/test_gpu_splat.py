@@ -293,3 +293,42 @@ def test_c1_matches_committed_golden(gpu, name):
     assert [int(v) for v in px[32 * 64 + 32, :4].view(np.uint32)] == g["pixel_32_32_xyzw_bits"]
     assert hashlib.sha256(np.ascontiguousarray(px[:, :4]).tobytes()).hexdigest() == g["pixels_sha256"]
     assert hashlib.sha256(film.resolve_rgb(1.0).tobytes()).hexdigest() == g["rgb_sha256"]
+
+
+@pytest.mark.parametrize("name,tile,spp,crop", [("gaussian", 16, 4, [0, 0, 1, 1]), ("mitchell", 16, 16, [0.1, 0.15, 0.9, 0.95]),
+                                                  ("lanczos", 24, 4, [0, 0, 1, 1]), ("box", 8, 4, [0, 0, 1, 1]),
+                                                  ("triangle", 16, 3, [0, 0, 1, 1])])
+def test_batched_tiles_equal_sequential_tiles(gpu, orc, name, tile, spp, crop):
+    """pbrt's workflow — many small tiles, each get_film_tile -> add_sample* -> merge_film_tile — in one call.
+    The oracle does it tile by tile in order; pixels in overlapping tile borders must still match bit for bit.
+    The triangle case uses radius 5 (outside the window kernel) and exercises the per-tile fallback."""
+    res = (150, 70)
+    radius = (5.0, 5.0) if name == "triangle" else None
+    filt, kind, rad, p0, p1 = make_filter(gpu, name, radius)
+    table = oracle.filter_table(orc, kind, rad, p0, p1)
+    film = gpu.Film.new(res, [[crop[0], crop[1]], [crop[2], crop[3]]], filt, 35.0, "x.pfm", 1.0, float("inf"))
+    of = OracleFilm(orc, res, crop, rad, table)
+    sbx = of.sample_bounds()
+    sbs = [(x, y, min(x + tile, sbx[2]), min(y + tile, sbx[3])) for y in range(sbx[1], sbx[3], tile) for x in range(sbx[0], sbx[2], tile)]
+    sbs.append((10, 10, 10, 20))  # an empty tile in the middle of the batch
+    rng = np.random.default_rng(2)
+    rng.shuffle(sbs)              # order matters where borders overlap; any order must work
+    xs, ls = [], []
+    for i, sb in enumerate(sbs):
+        xy, rgbw = oracle.synth_samples(orc, sb, spp, seed=i + 1)
+        xs.append(xy)
+        ls.append(rgbw)
+        t = of.get_film_tile(sb)
+        if len(xy):
+            orc.orc_ext_tile_add_samples(t, len(xy), oracle.fp(xy), oracle.fp(rgbw))
+        of.merge(t)
+    xy_all, rgbw_all = np.concatenate(xs), np.concatenate(ls)
+    for _ in range(2):  # twice: the second call accumulates on top and reuses the cached merge index
+        film.add_samples_tiles(sbs, spp, xy_all, rgbw_all, mode=gpu.SPLAT_EXACT)
+    film.check()
+    for i, sb in enumerate(sbs):
+        t = of.get_film_tile(sb)
+        if len(xs[i]):
+            orc.orc_ext_tile_add_samples(t, len(xs[i]), oracle.fp(xs[i]), oracle.fp(ls[i]))
+        of.merge(t)
+    assert np.array_equal(u32(film.read_pixels()), u32(of.pixels()))
