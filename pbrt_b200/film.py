@@ -245,9 +245,14 @@ class Film:
         """Many tiles in one call: tile i has sample bounds `sample_bounds[i]` (x0, y0, x1, y1) and its pixel-major
         samples start at `sample_offsets[i]` (default: tiles packed back to back).  Same result as calling
         add_samples_tile for each tile in order."""
-        sbs = np.ascontiguousarray([Bounds2i.of(b).as4() for b in sample_bounds], dtype=np.int32)
-        counts = np.array([max(b[2] - b[0], 0) * max(b[3] - b[1], 0) * spp for b in sbs], dtype=np.int64)
+        if isinstance(sample_bounds, np.ndarray) and sample_bounds.ndim == 2 and sample_bounds.shape[1] == 4:
+            sbs = np.ascontiguousarray(sample_bounds, dtype=np.int32)  # already flat {x0, y0, x1, y1} rows
+        else:
+            sbs = np.ascontiguousarray([Bounds2i.of(b).as4() for b in sample_bounds], dtype=np.int32)
         if sample_offsets is None:
+            w = np.maximum(sbs[:, 2].astype(np.int64) - sbs[:, 0], 0)
+            h = np.maximum(sbs[:, 3].astype(np.int64) - sbs[:, 1], 0)
+            counts = w * h * int(spp)
             sample_offsets = np.concatenate([[0], np.cumsum(counts)[:-1]])
         offs = np.ascontiguousarray(sample_offsets, dtype=np.int64)
         pxy, dev_a, k1 = as_pointer(xy)
