@@ -1319,12 +1319,11 @@ extern "C" int pbrt_synth_tiles(int32_t ntiles, const int64_t *offsets, const in
     cudaMemcpyAsync(d, offsets, (size_t)ntiles * sizeof(long long), cudaMemcpyHostToDevice, s);
     cudaMemcpyAsync(d + ntiles, counts, (size_t)ntiles * sizeof(long long), cudaMemcpyHostToDevice, s);
     int rc = PBRT_OK;
-    for (int t0 = 0; t0 < ntiles && rc == PBRT_OK; t0 += 65535) {
-        int nt = std::min(65535, ntiles - t0);
-        // tile indices are global: shift the seed-independent index through the pointer offset
-        if (t0 != 0) { rc = fail(PBRT_E_UNSUPPORTED, "more than 65535 tiles per call"); break; }
-        dim3 grid((unsigned)std::min<int64_t>((maxc + 255) / 256, 64), nt);
-        synth_tiles_kernel<<<grid, 256, 0, s>>>(nt, d, d + ntiles, seed, (float4 *)rgbw_dev);
+    if (ntiles > 65535) {
+        rc = fail(PBRT_E_UNSUPPORTED, "more than 65535 tiles per call");
+    } else {
+        dim3 grid((unsigned)std::min<int64_t>((maxc + 255) / 256, 64), ntiles);
+        synth_tiles_kernel<<<grid, 256, 0, s>>>(ntiles, d, d + ntiles, seed, (float4 *)rgbw_dev);
         ctx().launches++;
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) rc = pb::cuda_fail(e, "synth_tiles_kernel");

@@ -332,3 +332,32 @@ def test_batched_tiles_equal_sequential_tiles(gpu, orc, name, tile, spp, crop):
             orc.orc_ext_tile_add_samples(t, len(xs[i]), oracle.fp(xs[i]), oracle.fp(ls[i]))
         of.merge(t)
     assert np.array_equal(u32(film.read_pixels()), u32(of.pixels()))
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_configurations_exact(gpu, orc, seed):
+    """Randomised sweep: film size, crop window, filter, radius, spp, sample bounds (inside, straddling, outside)."""
+    rng = np.random.default_rng(1000 + seed)
+    name = list(oracle.FILTERS)[rng.integers(0, 5)]
+    r = float(rng.choice([0.5, 1.0, 1.25, 1.5, 2.0, 2.3, 2.5, 3.0, 3.7, 4.0, 4.49, 6.0]))
+    res = (int(rng.integers(8, 200)), int(rng.integers(8, 120)))
+    c = np.sort(rng.random(2) * 0.4)
+    crop = [float(c[0]), float(rng.random() * 0.3), float(1 - c[1] * 0.5), float(1 - rng.random() * 0.3)]
+    spp = int(rng.choice([1, 2, 3, 4, 8, 9, 16, 17]))
+    filt, kind, rad, p0, p1 = make_filter(gpu, name, (r, r))
+    table = oracle.filter_table(orc, kind, rad, p0, p1)
+    film = gpu.Film.new(res, [[crop[0], crop[1]], [crop[2], crop[3]]], filt, 35.0, "x.pfm", 1.0, float("inf"))
+    of = OracleFilm(orc, res, crop, rad, table)
+    assert film.cropped_pixel_bounds.as4() == of.cropped()
+    assert film.get_sample_bounds().as4() == of.sample_bounds()
+    for k in range(3):
+        x0, y0 = int(rng.integers(-10, res[0])), int(rng.integers(-10, res[1]))
+        sb = (x0, y0, x0 + int(rng.integers(1, res[0] + 10)), y0 + int(rng.integers(1, res[1] + 10)))
+        assert film._tile_bounds(sb)[0].as4() == of.tile_bounds(sb)
+        xy, rgbw = oracle.synth_samples(orc, sb, spp, seed=seed * 10 + k)
+        rgbw[:, 3] = rng.random(len(rgbw), dtype=np.float32) + 0.5
+        film.add_samples_tile(sb, spp, xy, rgbw, gpu.SPLAT_EXACT)
+        of.add_samples_pass(sb, spp, xy, rgbw, threads=4)
+    film.check()
+    assert np.array_equal(u32(film.read_pixels()), u32(of.pixels())), (name, r, res, crop, spp)
+    assert np.array_equal(u32(film.resolve_rgb(0.5)), u32(of.write_image_rgb(0.5)))
