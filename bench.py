@@ -48,6 +48,8 @@ WORKLOADS = {
                label="3840x2160 film, Mitchell r=2, one 16-spp pass of the 64 spp (BASELINE configs[2])"),
     "c5": dict(res=(7680, 4320), spp=16, filter="lanczos", radius=(4.0, 4.0), p0=3.0, p1=0.0,
                label="7680x4320 film, Lanczos-sinc r=4, one 16-spp pass of the 256 spp (BASELINE configs[4])"),
+    "c3_spp64": dict(res=(3840, 2160), spp=64, filter="mitchell", radius=(2.0, 2.0), p0=1 / 3, p1=1 / 3,
+                     label="3840x2160 film, Mitchell r=2, all 64 spp in one pixel-major pass (BASELINE configs[2])"),
     "c2_spp8": dict(res=(1920, 1080), spp=8, filter="gaussian", radius=(2.0, 2.0), p0=2.0, p1=0.0,
                     label="1920x1080 film, 8 spp per pass, Gaussian r=2 (occupancy experiment, not a BASELINE config)"),
     "c2_spp4": dict(res=(1920, 1080), spp=4, filter="gaussian", radius=(2.0, 2.0), p0=2.0, p1=0.0,
