@@ -39,6 +39,20 @@ def filter_table(filt: Filter) -> np.ndarray:
     return t
 
 
+def _pixel_major_spp(xy: np.ndarray, sb: Optional[Bounds2i]) -> int:
+    """spp if `xy` is a pixel-major stream over `sb` with the same count in every pixel, else 0."""
+    if sb is None or len(xy) == 0:
+        return 0
+    w, h = sb.p_max.x - sb.p_min.x, sb.p_max.y - sb.p_min.y
+    if w <= 0 or h <= 0 or len(xy) % (w * h):
+        return 0
+    spp = len(xy) // (w * h)
+    px = np.repeat(np.tile(np.arange(sb.p_min.x, sb.p_max.x), h), spp)
+    py = np.repeat(np.repeat(np.arange(sb.p_min.y, sb.p_max.y), w), spp)
+    ok = (xy[:, 0] >= px) & (xy[:, 0] <= px + 1) & (xy[:, 1] >= py) & (xy[:, 1] <= py + 1)
+    return spp if bool(ok.all()) else 0
+
+
 class FilmTilePixel:
     """film.rs:39-42 — a view of one pixel of a tile's buffer."""
 
@@ -187,7 +201,11 @@ class Film:
         if tile._samples_xy:  # EXTENSION: samples recorded through FilmTile.add_sample
             xy = np.asarray(tile._samples_xy, dtype=np.float32)
             rgbw = np.asarray(tile._samples_rgbw, dtype=np.float32)
-            self.add_samples(tile._sample_bounds, xy, rgbw)
+            spp = _pixel_major_spp(xy, tile._sample_bounds)
+            if spp:   # the order a renderer produces: the exact, order-preserving kernel applies
+                self.add_samples_tile(tile._sample_bounds, spp, xy, rgbw, SPLAT_EXACT)
+            else:     # any other order: scatter (order of additions not fixed)
+                self.add_samples(tile._sample_bounds, xy, rgbw)
             tile._samples_xy, tile._samples_rgbw = [], []
         _lib.check(
             _lib.lib.pbrt_film_merge_tile(

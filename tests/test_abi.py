@@ -139,3 +139,22 @@ def test_user_defined_filter_table(pb):
     t = pb.filter_table(Tent()).reshape(16, 16)
     assert t[0, 0] == np.float32((1 - 0.5 / 16) ** 2) or abs(t[0, 0] - (1 - 0.5 / 16) ** 2) < 1e-7
     assert np.allclose(t, t.T)
+
+
+def test_argument_errors_need_no_device(pb):
+    """Bad arguments are rejected before any CUDA call, with a message."""
+    import ctypes as C
+
+    from pbrt_b200 import _lib
+
+    L = _lib.lib
+    assert L.pbrt_film_merge_tile(None, _lib.i32x4((0, 0, 1, 1)), None, 0) == _lib.E_INVALID
+    assert "null" in _lib.last_error()
+    assert L.pbrt_film_check(None) == _lib.E_INVALID
+    assert L.pbrt_film_get_sample_bounds(None, _lib.i32x4((0, 0, 0, 0))) == _lib.E_INVALID
+    assert L.pbrt_film_add_samples_tile(None, _lib.i32x4((0, 0, 1, 1)), 1, None, None, 0, 0) == _lib.E_INVALID
+    assert L.pbrt_film_destroy(None) == _lib.OK  # Drop of nothing
+    h = C.c_void_p()
+    assert L.pbrt_filter_create(99, 1.0, 1.0, 0.0, 0.0, C.byref(h)) == _lib.E_INVALID
+    assert "unknown filter kind" in _lib.last_error()
+    assert L.pbrt_filter_table(None, None) == _lib.E_INVALID

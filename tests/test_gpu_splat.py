@@ -361,3 +361,65 @@ def test_random_configurations_exact(gpu, orc, seed):
     film.check()
     assert np.array_equal(u32(film.read_pixels()), u32(of.pixels())), (name, r, res, crop, spp)
     assert np.array_equal(u32(film.resolve_rgb(0.5)), u32(of.write_image_rgb(0.5)))
+
+
+@pytest.mark.parametrize("name,res,band", [("mitchell", (3840, 2160), (1000, 1012)), ("lanczos", (7680, 4320), (4312, 4320))])
+def test_full_size_c3_c5_band_exact(gpu, orc, name, res, band):
+    """BASELINE configs[2] and [4] at full film size (one 16-spp pass, as the stream is fed): a band of rows
+    against the oracle bit for bit (for C5 the band touches the bottom edge of the film), run-to-run determinism,
+    and the sharded run (8 row shards, as on 8 GPUs) equal to the single film."""
+    from pbrt_b200 import dist as pdist
+    from pbrt_b200 import synth
+
+    spp = 16
+    filt, kind, rad, p0, p1 = make_filter(gpu, name)
+    table = oracle.filter_table(orc, kind, rad, p0, p1)
+    full = (0, 0, *res)
+    xy_d, rgbw_d, n = synth.samples(full, spp, seed=1)
+    film = gpu.Film.new(res, [[0, 0], [1, 1]], filt, 35.0, "x.pfm", 1.0, float("inf"))
+    film.add_samples_tile(full, spp, xy_d, rgbw_d, gpu.SPLAT_EXACT)
+    film.check()
+    ref = film.resolve_rgb(1.0).reshape(res[1], res[0], 3)
+    px = film.read_pixels().reshape(res[1], res[0], 7)
+    y0, y1 = band
+    halo = pdist.halo_rows(rad[1]) + 1
+    sb = (0, max(0, y0 - halo), res[0], min(res[1], y1 + halo))
+    xy_b, rgbw_b, nb = synth.samples(sb, spp, seed=1, index_bounds=full)
+    of = OracleFilm(orc, res, [0, y0 / res[1], 1, y1 / res[1]], rad, table)
+    assert of.cropped() == (0, y0, res[0], y1)
+    of.add_samples_pass(sb, spp, xy_b.to_numpy(np.float32, (nb, 2)), rgbw_b.to_numpy(np.float32, (nb, 4)), threads=8)
+    assert np.array_equal(u32(px[y0:y1].reshape(-1, 7)), u32(of.pixels()))
+    del px
+    # the same frame from 8 row shards, each fed its rows + halo
+    world = 8
+    for rank in (0, 3, 7):
+        f = gpu.Film.new(res, [[0, 0], [1, 1]], filt, 35.0, "x.pfm", 1.0, float("inf"), rank=rank, nranks=world)
+        ob = f.owned_pixel_bounds
+        ssb = pdist.shard_sample_bounds(film.cropped_pixel_bounds, (ob.p_min.y, ob.p_max.y), rad[1])
+        sxy, srgbw, sn = synth.samples(ssb.as4(), spp, seed=1, index_bounds=full)
+        f.add_samples_tile(ssb.as4(), spp, sxy, srgbw, gpu.SPLAT_EXACT)
+        f.check()
+        got = f.resolve_rgb(1.0).reshape(-1, res[0], 3)
+        assert np.array_equal(u32(got), u32(ref[ob.p_min.y:ob.p_max.y])), rank
+        f.close()
+        del sxy, srgbw
+
+
+def test_filmtile_add_sample_in_renderer_order_is_exact(gpu, orc):
+    """FilmTile.add_sample on the host mirror: samples recorded in pixel-major order go through the exact kernel."""
+    res, spp = (24, 18), 4
+    filt, kind, rad, p0, p1 = make_filter(gpu, "mitchell")
+    table = oracle.filter_table(orc, kind, rad, p0, p1)
+    film = gpu.Film.new(res, [[0, 0], [1, 1]], filt, 35.0, "x.pfm", 1.0, float("inf"))
+    of = OracleFilm(orc, res, [0, 0, 1, 1], rad, table)
+    sb = (2, 3, 20, 15)
+    xy, rgbw = oracle.synth_samples(orc, sb, spp)
+    tile = film.get_film_tile([[sb[0], sb[1]], [sb[2], sb[3]]])
+    ot = of.get_film_tile(sb)
+    for p, l in zip(xy, rgbw):
+        tile.add_sample(p, l[:3], float(l[3]))
+        orc.orc_ext_tile_add_sample(ot, float(p[0]), float(p[1]), oracle.farr(l[:3]), float(l[3]))
+    film.merge_film_tile(tile)
+    of.merge(ot)
+    film.check()
+    assert np.array_equal(u32(film.read_pixels()), u32(of.pixels()))
