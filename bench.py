@@ -422,6 +422,11 @@ def main():
         }
         if extras:
             out["extras"] = extras
+            # the second half of BASELINE.json's metric ("+ texture lookups/s ... % HBM peak"), N = 1 only
+            tf, tr = extras.get("texture_constant_f32"), extras.get("texture_constant_rgb")
+            if isinstance(tf, dict) and "lookups_per_s" in tf:
+                out["texture_lookups_per_s"] = {"constant_f32": tf["lookups_per_s"], "constant_f32_frac_of_hbm_peak": tf["frac"],
+                                                "constant_rgb": tr["lookups_per_s"], "constant_rgb_frac_of_hbm_peak": tr["frac"]}
         emit(out)
     if world > 1:
         dist.destroy_process_group()
