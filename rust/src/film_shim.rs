@@ -1,6 +1,6 @@
-//! film.rs — UNTESTED SOURCE (no rustc/cargo in the build image).
+//! film_shim.rs — UNTESTED SOURCE (no rustc/cargo in the build image).
 //!
-//! Drop-in replacement for the reference's src/core/film.rs: every `pub` item keeps its signature
+//! Drop-in replacement for the reference's src/core/film.rs (install it under that name): every `pub` item keeps its signature
 //! (reference lines cited), the pixel storage moves to HBM behind a `PbrtFilm*`, and both hot loops
 //! (`merge_film_tile` :313-326, `write_image` :340-372) become one FFI call each.
 use log::info;
