@@ -14,8 +14,13 @@
  *     src/core/spectrum.rs:151-153).  The f64 / sampled-spectrum builds are not supported.
  *   - bounds are int32 {x0, y0, x1, y1}, max exclusive (Bounds2i, src/core/geometry/bounds.rs).
  *     The reference uses isize; a host shim must range-check before narrowing.
- *   - `*_is_device` = 0: pointer is host memory, the call copies; 1: pointer is device memory
- *     on the film's device and is used in place.
+ *   - `*_is_device` = 0 (PBRT_MEM_HOST): pointer is host memory, the call copies and, for outputs,
+ *     returns when the data has arrived; 1 (PBRT_MEM_DEVICE): pointer is device memory on the film's
+ *     device and is used in place; 2 (PBRT_MEM_PINNED_ASYNC, accepted by add_samples_tile and
+ *     resolve_rgb / resolve_rgb8): pointer is page-locked host memory and the transfer is only
+ *     enqueued — inputs are double-buffered on a copy stream so that the upload of one call overlaps
+ *     the kernels of the previous one; the caller keeps the buffers untouched until
+ *     pbrt_b200_synchronize().
  *   - work is ordered on one stream per process (pbrt_b200_set_stream); calls that return data
  *     to the host synchronise that stream, the others are asynchronous.
  *   - there is no CPU fallback: every compute entry point fails with PBRT_E_CUDA when no
@@ -46,6 +51,8 @@ typedef enum {
 } PbrtStatus;
 
 #define PBRT_FILTER_TABLE_WIDTH 16 /* src/core/film.rs:34 */
+
+enum { PBRT_MEM_HOST = 0, PBRT_MEM_DEVICE = 1, PBRT_MEM_PINNED_ASYNC = 2 };
 
 typedef struct PbrtFilm PbrtFilm;     /* src/core/film.rs:59-76 — device-resident */
 typedef struct PbrtFilter PbrtFilter; /* src/core/filter.rs:22-29 — host object */

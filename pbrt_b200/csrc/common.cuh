@@ -113,6 +113,12 @@ struct PbrtFilm {
     int64_t idx_need;        // pixels the batch's rgbw buffer must hold
     void *d_tile_desc;       // add_samples_tiles: SplatTile array (grow-only)
     size_t tile_desc_bytes;
+    // PBRT_MEM_PINNED_ASYNC inputs: two staging sets filled on the copy stream while the other is consumed
+    void *d_pipe[2][2];      // [set][0 = xy, 1 = rgbw]
+    size_t pipe_bytes[2][2];
+    cudaEvent_t ev_staged[2], ev_consumed[2];
+    bool pipe_ready;
+    int pipe_turn;
 };
 
 namespace pb {
@@ -122,6 +128,7 @@ struct Ctx {
     int device;
     int sm_count;
     cudaStream_t own_stream;
+    cudaStream_t copy_stream;  // uploads of PBRT_MEM_PINNED_ASYNC inputs
     cudaStream_t stream;
     uint64_t launches;
 };

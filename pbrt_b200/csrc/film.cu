@@ -21,7 +21,7 @@ namespace pb {
 static thread_local char g_err[512] = "";
 
 Ctx &ctx() {
-    static Ctx c = {false, -1, 0, nullptr, nullptr, 0};
+    static Ctx c = {false, -1, 0, nullptr, nullptr, nullptr, 0};
     return c;
 }
 
@@ -109,7 +109,10 @@ extern "C" int pbrt_b200_init(int device) {
                     p.minor);
     pb::Ctx &c = ctx();
     if (c.ready && c.device == device) return PBRT_OK;
-    if (!c.own_stream || c.device != device) PB_CUDA(cudaStreamCreateWithFlags(&c.own_stream, cudaStreamNonBlocking));
+    if (!c.own_stream || c.device != device) {
+        PB_CUDA(cudaStreamCreateWithFlags(&c.own_stream, cudaStreamNonBlocking));
+        PB_CUDA(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
+    }
     c.stream = c.own_stream;
     c.device = device;
     c.sm_count = p.multiProcessorCount;
@@ -125,6 +128,7 @@ extern "C" int pbrt_b200_set_stream(void *s) {
 
 extern "C" int pbrt_b200_synchronize(void) {
     if (int rc = pb::ensure_ready()) return rc;
+    PB_CUDA(cudaStreamSynchronize(ctx().copy_stream));
     PB_CUDA(cudaStreamSynchronize(ctx().stream));
     return PBRT_OK;
 }
@@ -367,7 +371,7 @@ extern "C" int pbrt_film_create_sharded(int32_t xres, int32_t yres, const float 
 
 extern "C" int pbrt_film_destroy(PbrtFilm *f) {
     if (!f) return PBRT_OK;
-    if (ctx().ready) cudaStreamSynchronize(ctx().stream);
+    if (ctx().ready) { cudaStreamSynchronize(ctx().copy_stream); cudaStreamSynchronize(ctx().stream); }
     cudaFree(f->d_xyzw);
     cudaFree(f->d_splat);
     cudaFree(f->d_table);
@@ -377,6 +381,11 @@ extern "C" int pbrt_film_destroy(PbrtFilm *f) {
     cudaFree(f->d_scratch_tile);
     cudaFree(f->d_idx);
     cudaFree(f->d_tile_desc);
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(f->d_pipe[i][0]);
+        cudaFree(f->d_pipe[i][1]);
+        if (f->pipe_ready) { cudaEventDestroy(f->ev_staged[i]); cudaEventDestroy(f->ev_consumed[i]); }
+    }
     free(f->idx_bounds);
     free(f->idx_offsets);
     cudaGetLastError();
@@ -750,7 +759,8 @@ static int resolve_impl(const PbrtFilm *f, float splat_scale, void *out, int dst
     if (f->npix == 0) return PBRT_OK;
     const size_t bytes = (size_t)f->npix * 3 * (BYTES ? 1 : sizeof(float));
     void *d_out = out;
-    if (!dst_is_device) {
+    const bool to_host = dst_is_device != PBRT_MEM_DEVICE;
+    if (to_host) {
         if (int rc = pb::out_stage(bytes, &d_out)) return rc;
     } else if (((uintptr_t)out & 15) != 0) {
         return fail(PBRT_E_INVALID, "device output must be 16-byte aligned");
@@ -759,9 +769,10 @@ static int resolve_impl(const PbrtFilm *f, float splat_scale, void *out, int dst
     resolve_kernel<BYTES><<<blocks, RES_PIX, 0, ctx().stream>>>(f->d_xyzw, f->d_splat, (long long)f->npix,
                                                                 splat_scale, f->scale, d_out);
     PB_LAUNCH_CHECK("resolve_kernel");
-    if (!dst_is_device) {
+    if (to_host) {
         PB_CUDA(cudaMemcpyAsync(out, d_out, bytes, cudaMemcpyDeviceToHost, ctx().stream));
-        PB_CUDA(cudaStreamSynchronize(ctx().stream));
+        // PBRT_MEM_PINNED_ASYNC: the read-back is only enqueued; pbrt_b200_synchronize() completes it
+        if (dst_is_device != PBRT_MEM_PINNED_ASYNC) PB_CUDA(cudaStreamSynchronize(ctx().stream));
     }
     return PBRT_OK;
 }
@@ -1065,6 +1076,38 @@ extern "C" int pbrt_film_add_samples_tile(PbrtFilm *f, const int32_t sbv[4], int
     const size_t n = (size_t)pb::bw(sb) * pb::bh(sb) * (size_t)spp;
     const float2 *d_xy = (const float2 *)xy;
     const float4 *d_rgbw = (const float4 *)rgbw;
+    if (src_is_device == PBRT_MEM_PINNED_ASYNC) {
+        // upload on the copy stream into the staging set the previous-but-one call used; the kernel waits for
+        // the upload, the next upload into this set waits for the kernel
+        if (!f->pipe_ready) {
+            for (int i = 0; i < 2; ++i) {
+                PB_CUDA(cudaEventCreateWithFlags(&f->ev_staged[i], cudaEventDisableTiming));
+                PB_CUDA(cudaEventCreateWithFlags(&f->ev_consumed[i], cudaEventDisableTiming));
+            }
+            f->pipe_ready = true;
+        }
+        const int set = f->pipe_turn;
+        f->pipe_turn ^= 1;
+        const size_t need[2] = {n * sizeof(float2), n * sizeof(float4)};
+        for (int k = 0; k < 2; ++k) {
+            if (need[k] > f->pipe_bytes[set][k]) {
+                cudaFree(f->d_pipe[set][k]);  // synchronises the device: nothing is using the old buffer
+                f->d_pipe[set][k] = nullptr;
+                f->pipe_bytes[set][k] = 0;
+                PB_CUDA(cudaMalloc(&f->d_pipe[set][k], need[k] + 256));
+                f->pipe_bytes[set][k] = need[k] + 256;
+            }
+        }
+        cudaStream_t cs = ctx().copy_stream;
+        PB_CUDA(cudaStreamWaitEvent(cs, f->ev_consumed[set], 0));
+        PB_CUDA(cudaMemcpyAsync(f->d_pipe[set][0], xy, need[0], cudaMemcpyHostToDevice, cs));
+        PB_CUDA(cudaMemcpyAsync(f->d_pipe[set][1], rgbw, need[1], cudaMemcpyHostToDevice, cs));
+        PB_CUDA(cudaEventRecord(f->ev_staged[set], cs));
+        PB_CUDA(cudaStreamWaitEvent(ctx().stream, f->ev_staged[set], 0));
+        int rc = pb::launch_splat_tile(f, sb, tb, spp, (const float2 *)f->d_pipe[set][0], (const float4 *)f->d_pipe[set][1], mode);
+        PB_CUDA(cudaEventRecord(f->ev_consumed[set], ctx().stream));
+        return rc;
+    }
     if (!src_is_device) {
         void *a, *b;
         if (int rc = pb::stage_in(f, 0, xy, n * sizeof(float2), &a)) return rc;

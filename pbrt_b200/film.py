@@ -247,16 +247,22 @@ class Film:
         )
 
     # ------------------------------------------------------------------ EXTENSION: sample splatting
-    def add_samples_tile(self, sample_bounds, spp: int, xy, rgbw, mode: int = SPLAT_EXACT) -> None:
+    def add_samples_tile(self, sample_bounds, spp: int, xy, rgbw, mode: int = SPLAT_EXACT, pinned_async: bool = False) -> None:
         """get_film_tile(sample_bounds) -> add_sample for each sample -> merge_film_tile, on the device.
 
         Samples are pixel-major over `sample_bounds`, `spp` per pixel, each inside its pixel.
+        `pinned_async`: xy / rgbw are page-locked host arrays (PinnedBuffer.array); the upload is enqueued on
+        the copy stream and overlaps the previous call's kernels; keep the arrays untouched until synchronize().
         """
         sb = Bounds2i.of(sample_bounds)
         pxy, dev_a, k1 = as_pointer(xy)
         prgbw, dev_b, k2 = as_pointer(rgbw)
         if dev_a != dev_b:
             raise ValueError("xy and rgbw must both be host or both be device buffers")
+        if pinned_async:
+            if dev_a:
+                raise ValueError("pinned_async is for host arrays")
+            dev_a = 2  # PBRT_MEM_PINNED_ASYNC
         _lib.check(_lib.lib.pbrt_film_add_samples_tile(self._h, _lib.i32x4(sb.as4()), int(spp), pxy, prgbw, dev_a, int(mode)))
 
     def add_samples_tiles(self, sample_bounds, spp: int, xy, rgbw, sample_offsets=None, mode: int = SPLAT_EXACT) -> None:
@@ -317,12 +323,17 @@ class Film:
         _lib.check(_lib.lib.pbrt_film_clear(self._h))
 
     # ------------------------------------------------------------------ write_image (film.rs:340-383)
-    def resolve_rgb(self, splat_scale: float = 1.0, out=None) -> np.ndarray:
-        """The rgb buffer `write_image` builds (film.rs:342-372): (owned pixels, 3) f32."""
+    def resolve_rgb(self, splat_scale: float = 1.0, out=None, pinned_async: bool = False) -> np.ndarray:
+        """The rgb buffer `write_image` builds (film.rs:342-372): (owned pixels, 3) f32.
+
+        `pinned_async`: `out` is a page-locked host array and the read-back is only enqueued (synchronize() completes it).
+        """
         n = max(self.owned_pixel_bounds.area(), 0)
         if out is None:
             out = np.empty((n, 3), dtype=np.float32)
         ptr, is_dev, keep = as_pointer(out)
+        if pinned_async and not is_dev:
+            is_dev = 2  # PBRT_MEM_PINNED_ASYNC
         _lib.check(_lib.lib.pbrt_film_resolve_rgb(self._h, float(splat_scale), ptr, is_dev))
         return out
 

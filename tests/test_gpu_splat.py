@@ -423,3 +423,30 @@ def test_filmtile_add_sample_in_renderer_order_is_exact(gpu, orc):
     of.merge(ot)
     film.check()
     assert np.array_equal(u32(film.read_pixels()), u32(of.pixels()))
+
+
+def test_pinned_async_pipeline_equals_synchronous_calls(gpu, orc):
+    """PBRT_MEM_PINNED_ASYNC: uploads double-buffered on the copy stream, read-back enqueued; same film, same frames."""
+    res, spp = (128, 96), 4
+    filt, kind, rad, p0, p1 = make_filter(gpu, "gaussian")
+    a = gpu.Film.new(res, [[0, 0], [1, 1]], filt, 35.0, "x.pfm", 1.0, float("inf"))
+    b = gpu.Film.new(res, [[0, 0], [1, 1]], filt, 35.0, "x.pfm", 1.0, float("inf"))
+    n = res[0] * res[1] * spp
+    hx = [gpu.PinnedBuffer(np.float32, (n, 2)) for _ in range(3)]
+    hl = [gpu.PinnedBuffer(np.float32, (n, 4)) for _ in range(3)]
+    outs = [gpu.PinnedBuffer(np.float32, (res[0] * res[1], 3)) for _ in range(3)]
+    want = []
+    for i in range(3):
+        xy, rgbw = oracle.synth_samples(orc, (0, 0, *res), spp, seed=i + 1)
+        hx[i].array[:] = xy
+        hl[i].array[:] = rgbw
+        a.add_samples_tile((0, 0, *res), spp, xy, rgbw, gpu.SPLAT_EXACT)
+        want.append(a.resolve_rgb(1.0).copy())
+    for i in range(3):  # nothing waits in between: three uploads, kernels and read-backs in flight
+        b.add_samples_tile((0, 0, *res), spp, hx[i].array, hl[i].array, gpu.SPLAT_EXACT, pinned_async=True)
+        b.resolve_rgb(1.0, out=outs[i].array, pinned_async=True)
+    gpu.synchronize()
+    b.check()
+    for i in range(3):
+        assert np.array_equal(u32(outs[i].array), u32(want[i])), i
+    assert np.array_equal(u32(a.read_pixels()), u32(b.read_pixels()))
