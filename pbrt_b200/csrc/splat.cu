@@ -372,7 +372,9 @@ __global__ void __launch_bounds__(TW) splat_window_kernel(SplatParams P) {
                         const u64 Lb1 = pack2(a.z, 1.f);
 #pragma unroll
                         for (int j = 0; j < ROWS; ++j) {
-                            const u64 ww = lds_pair(xcol + rb_byte(yb, j) * TAB_ROW_BYTES);
+                            // row byte j times the table's row pitch, plus the column address, in one dot-product
+                            // instruction: dp4a(bytes, pitch in byte lane j, xcol)
+                            const u64 ww = lds_pair(__dp4a(rb_word(yb, j >> 2), (unsigned)TAB_ROW_BYTES << (8 * (j & 3)), xcol));
                             acc_rg[j] = accumulate<FMA>(acc_rg[j], Lrg, ww, negzero);
                             if (FMA) {
                                 acc_bw[j] = fma2(Lb1, ww, acc_bw[j]);
