@@ -158,3 +158,13 @@ def test_argument_errors_need_no_device(pb):
     assert L.pbrt_filter_create(99, 1.0, 1.0, 0.0, 0.0, C.byref(h)) == _lib.E_INVALID
     assert "unknown filter kind" in _lib.last_error()
     assert L.pbrt_filter_table(None, None) == _lib.E_INVALID
+
+
+def test_header_is_valid_c_and_cpp(tmp_path):
+    """include/pbrt_b200.h is a C header (the FFI boundary): it must compile as C11 and as C++17."""
+    c = tmp_path / "t.c"
+    c.write_text('#include "pbrt_b200.h"\nint main(void) { int (*f)(void) = pbrt_b200_version; return f != 0 ? 0 : 1; }\n')
+    subprocess.run(["gcc", "-std=c11", "-Wall", "-Werror", "-fsyntax-only", f"-I{ROOT / 'include'}", str(c)], check=True)
+    cpp = tmp_path / "t.cpp"
+    cpp.write_text('#include "pbrt_b200.hpp"\nint main() { pbrt::Bounds2i b = pbrt::Bounds2i::from({0, 0}, {2, 2}); return b.area() == 4 ? 0 : 1; }\n')
+    subprocess.run(["g++", "-std=c++17", "-Wall", "-Werror", "-fsyntax-only", f"-I{ROOT / 'include'}", str(cpp)], check=True)
