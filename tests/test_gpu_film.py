@@ -263,3 +263,32 @@ def test_resolve_rgb8_at_every_byte_threshold(gpu, orc):
     assert np.array_equal(got, want)
     # and the thresholds themselves, fed as grey pixels with weight 1 straight into the film (xyz_to_rgb(to_xyz(v,v,v)) ~ v)
     assert len(np.unique(got)) > 200
+
+
+def test_merge_and_resolve_special_values_bitwise(gpu, orc):
+    """NaN, +-Inf, denormals, +-0 and huge values through merge_film_tile and the write_image loop: same bits as the CPU."""
+    res = (64, 8)
+    film = gpu.Film.new(res, [[0, 0], [1, 1]], gpu.BoxFilter.new([0.5, 0.5]), 35.0, "x.pfm", 1.5, float("inf"))
+    of = OracleFilm(orc, res, [0, 0, 1, 1], (0.5, 0.5), np.ones(256, np.float32), scale=1.5)
+    specials = np.array([0.0, -0.0, 1e-45, -1e-45, 1e-38, 3.4e38, -3.4e38, np.inf, -np.inf, np.nan, 1.0, -1.0, 0.5, 1e-20, 123456.78, 7e-8],
+                        dtype=np.float32)
+    rng = np.random.default_rng(9)
+    for _ in range(3):
+        t, ot = film.get_film_tile([[0, 0], list(res)]), of.get_film_tile((0, 0, *res))
+        vals = rng.choice(specials, size=(len(t.pixels), 4)).astype(np.float32)
+        t.pixels[:] = vals
+        of.tile_pixels(ot)[:] = vals
+        film.merge_film_tile(t)
+        of.merge(ot)
+    a, b = film.read_pixels(), of.pixels()
+    # NaN payloads may differ between x86 and the GPU; compare NaN-ness, and bits everywhere else
+    assert np.array_equal(np.isnan(a), np.isnan(b))
+    m = ~np.isnan(b)
+    assert np.array_equal(a.view(np.uint32)[m], b.view(np.uint32)[m])
+    ra, rb = film.resolve_rgb(0.75), of.write_image_rgb(0.75)
+    assert np.array_equal(np.isnan(ra), np.isnan(rb))
+    m = ~np.isnan(rb)
+    assert np.array_equal(ra.view(np.uint32)[m], rb.view(np.uint32)[m])
+    got8 = film.resolve_rgb8(0.75).reshape(-1)
+    want8 = np.array([orc.orc_to_byte(float(v)) for v in rb.reshape(-1)], dtype=np.uint8)
+    assert np.array_equal(got8, want8)
