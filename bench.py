@@ -325,7 +325,7 @@ def main():
         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
         "traffic": measured_traffic(args.workload, args.mode) if world == 1 else None, "peak_source": peak_src, "kernel": "splat_window_kernel" if args.mode != "atomic" else "splat_atomic_kernel",
         "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kern_ms, "kernel_ms_min": min(per_step),
-        "note": "24 B/sample read + 32 B/film pixel RMW per launch; the kernel is issue-bound, not HBM-bound (DESIGN.md)",
+        "note": "24 B/sample read + 32 B/film pixel RMW per launch; the splat is bound by shared-memory load latency and instruction issue, not by HBM (DESIGN.md section 5, profiles/)",
     }
 
     # ---- final assembly (once per render, not per step) ----------------------------------
