@@ -173,8 +173,15 @@ struct WinCfg {
 // column adds an exact zero there (x + 0 == x for every finite x), which keeps the inner loop free of
 // branches.  The odd row pitch also spreads equal columns of different rows over different banks.
 constexpr int TAB_ZERO = 16;
-constexpr int TAB_ROW_BYTES = 17 * 8;
-constexpr int WIN_TABLE_BYTES = 2432;  // >= 17 * TAB_ROW_BYTES, multiple of 128
+// Row pitch.  The lanes of a warp hold sample s of neighbouring pixels; for stratified streams their
+// (row, column) table indices differ by at most 2 each.  With a pitch of 21 entries (21 = 5 mod 16
+// eight-byte bank slots) 5*drow + dcol is never 0 mod 16 in that range, so the lookups of a warp fall
+// on distinct banks (a pitch of 17 made (row, col) collide with (row+1, col-1): 30 % extra wavefronts).
+// h = 4 keeps 17: its larger records leave no room for the bigger table without losing a CTA per SM.
+template <int H> struct TabCfg {
+    static constexpr int ROW_BYTES = (H == 4 ? 17 : 21) * 8;
+    static constexpr int BYTES = (17 * ROW_BYTES + 127) / 128 * 128;
+};
 
 // shared-memory layout for one sample row of a CTA strip.  The pixel pitch is odd (in elements)
 // so that lanes reading sample s of consecutive pixels fall on distinct banks for 4/8/16-byte loads.
@@ -183,7 +190,7 @@ struct WinSmem {
     static constexpr int NPX = TW + 2 * H;
     __host__ __device__ static int pitch(int spp) { return spp | 1; }
     __host__ __device__ static size_t bytes(int spp) {
-        return WIN_TABLE_BYTES + (size_t)NPX * pitch(spp) * (16 + sizeof(typename WinCfg<H>::RB));
+        return TabCfg<H>::BYTES + (size_t)NPX * pitch(spp) * (16 + sizeof(typename WinCfg<H>::RB));
     }
 };
 
@@ -228,6 +235,8 @@ __global__ void __launch_bounds__(TW) splat_window_kernel(SplatParams P) {
     typedef typename WinCfg<H>::RB RB;
     constexpr int NPX = WinSmem<H, TW>::NPX;
     extern __shared__ __align__(16) unsigned char smem[];
+    constexpr int TAB_ROW_BYTES = TabCfg<H>::ROW_BYTES;
+    constexpr int WIN_TABLE_BYTES = TabCfg<H>::BYTES;
     float4 *s_a = reinterpret_cast<float4 *>(smem + WIN_TABLE_BYTES);
     const int pitch = WinSmem<H, TW>::pitch(P.spp);
     RB *s_b = reinterpret_cast<RB *>(smem + WIN_TABLE_BYTES + (size_t)NPX * pitch * 16);
