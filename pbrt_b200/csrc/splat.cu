@@ -17,7 +17,10 @@
 //     one per byte (0xFF = row outside the footprint).  Records go to shared memory with a padded
 //     pixel pitch so that lanes reading sample s of consecutive pixels hit distinct banks.
 //     The gather then costs, per (sample, column): one LDS.128 + one LDS.32/64, the ifx index
-//     (5 FP ops), and per covered row PRMT + LEA + LDS(table) + 4 packed f32x2 ops.
+//     (5 FP ops), and per window row one IDP.4A (table address) + LDS(table) + 3 FMUL + 2 FADD2
+//     (exact) or 2 FFMA2 (PBRT_SPLAT_FMA).  ptxas fuses a packed mul feeding a packed add into one
+//     FFMA2 even under --fmad=false, so the exact variant multiplies in scalar registers and only
+//     adds packed (tests/test_abi.py checks the SASS).
 //     When the oldest window row can no longer be reached it is converted (rgb_to_xyz) and
 //     added to the film: one float4 read-modify-write per pixel per call.
 //
@@ -29,8 +32,11 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <type_traits>
 
 #include "common.cuh"
+
+#include <type_traits>
 
 namespace pb {
 
@@ -47,7 +53,6 @@ struct SplatParams {
     float4 *film;
     int *err;
     int rows_per_cta;
-    unsigned negzero_bits;  // 0x80000000, passed at run time so ptxas cannot constant-fold it (see accumulate())
     // batched mode (pbrt_film_add_samples_tiles): blockIdx.z selects a tile; its bounds and streams replace
     // sb / tb / xy / rgbw, and finished pixels go to the tile's own RGBW buffer instead of the film
     const SplatTile *tiles;
@@ -127,9 +132,13 @@ __global__ void __launch_bounds__(256) splat_gather_generic_kernel(SplatParams P
 // ---- window gather -----------------------------------------------------------------------
 
 #ifndef PBRT_WIN_UNROLL
-#define PBRT_WIN_UNROLL 4
+#define PBRT_WIN_UNROLL 8
 #endif
-constexpr int kWinUnroll = PBRT_WIN_UNROLL;  // samples per trip of the gather's inner loop
+constexpr int kWinUnroll = PBRT_WIN_UNROLL;
+#ifndef PBRT_WIN_INTERIOR_UNROLL
+#define PBRT_WIN_INTERIOR_UNROLL 1
+#endif
+constexpr int kWinInteriorUnroll = PBRT_WIN_INTERIOR_UNROLL;  // 1 = keep the interior-column loop rolled (smaller code)  // samples per trip of the gather's inner loop
 
 typedef unsigned long long u64;
 
@@ -168,29 +177,31 @@ struct WinCfg {
     typedef typename RowBytes<NW>::T RB;
 };
 
-// Filter table in shared memory: 17 rows x 17 entries of (w, w) — every weight twice, so one LDS.64
-// yields the packed operand.  Row 16 and column 16 are zero: a sample that does not reach a row /
+// Filter table in shared memory: 17 rows x 17 entries.  Row 16 and column 16 are zero: a sample that does not reach a row /
 // column adds an exact zero there (x + 0 == x for every finite x), which keeps the inner loop free of
 // branches.  The odd row pitch also spreads equal columns of different rows over different banks.
 constexpr int TAB_ZERO = 16;
 // Row pitch.  The lanes of a warp hold sample s of neighbouring pixels; for stratified streams their
-// (row, column) table indices differ by at most 2 each.  With a pitch of 21 entries (21 = 5 mod 16
-// eight-byte bank slots) 5*drow + dcol is never 0 mod 16 in that range, so the lookups of a warp fall
-// on distinct banks (a pitch of 17 made (row, col) collide with (row+1, col-1): 30 % extra wavefronts).
-// h = 4 keeps 17: its larger records leave no room for the bigger table without losing a CTA per SM.
-template <int H> struct TabCfg {
-    static constexpr int ROW_BYTES = (H == 4 ? 17 : 21) * 8;
+// (row, column) table indices differ by at most 2 each.  With a pitch of 21 entries, 21*drow + dcol is
+// never 0 modulo the 32 four-byte (or 16 eight-byte) bank slots in that range, so the lookups of a warp
+// fall on distinct banks (a pitch of 17 made (row, col) collide with (row+1, col-1): 30 % extra wavefronts).
+// Entries are (w, w) pairs (8 B) for the FMA variant, whose FFMA2 wants the packed operand, and single
+// weights (4 B) for the exact variant: half the shared-memory wavefronts per lookup.  The h = 4 FMA
+// variant keeps pitch 17: its larger records leave no room for the bigger table without losing a CTA per SM.
+template <int H, bool FMA> struct TabCfg {
+    static constexpr int ENTRY = FMA ? 8 : 4;
+    static constexpr int ROW_BYTES = ((H == 4 && FMA) ? 17 : 21) * ENTRY;
     static constexpr int BYTES = (17 * ROW_BYTES + 127) / 128 * 128;
 };
 
 // shared-memory layout for one sample row of a CTA strip.  The pixel pitch is odd (in elements)
 // so that lanes reading sample s of consecutive pixels fall on distinct banks for 4/8/16-byte loads.
-template <int H, int TW>
+template <int H, int TW, bool FMA>
 struct WinSmem {
     static constexpr int NPX = TW + 2 * H;
     __host__ __device__ static int pitch(int spp) { return spp | 1; }
     __host__ __device__ static size_t bytes(int spp) {
-        return TabCfg<H>::BYTES + (size_t)NPX * pitch(spp) * (16 + sizeof(typename WinCfg<H>::RB));
+        return TabCfg<H, FMA>::BYTES + (size_t)NPX * pitch(spp) * (16 + sizeof(typename WinCfg<H>::RB));
     }
 };
 
@@ -219,13 +230,10 @@ __device__ __forceinline__ u64 lds_pair(unsigned addr) {
     return v;
 }
 
-// acc += L * (w, w).  Exact mode: the product is formed as fma(L, w, -0), which rounds exactly like a
-// multiply, with the -0 operand held in a register whose value ptxas cannot see (it would otherwise
-// fold fma+add or mul+add into a single FFMA2, which rounds once instead of twice).
-template <bool FMA>
-__device__ __forceinline__ u64 accumulate(u64 acc, u64 L, u64 ww, u64 negzero) {
-    if (FMA) return fma2(L, ww, acc);
-    return add2(acc, fma2(L, ww, negzero));
+__device__ __forceinline__ float lds_f32(unsigned addr) {
+    float v;
+    asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
 }
 
 template <int H, int TW, bool FMA>
@@ -233,12 +241,13 @@ __global__ void __launch_bounds__(TW) splat_window_kernel(SplatParams P) {
     constexpr int ROWS = WinCfg<H>::ROWS;
     constexpr int NW = WinCfg<H>::NW;
     typedef typename WinCfg<H>::RB RB;
-    constexpr int NPX = WinSmem<H, TW>::NPX;
+    constexpr int NPX = WinSmem<H, TW, FMA>::NPX;
     extern __shared__ __align__(16) unsigned char smem[];
-    constexpr int TAB_ROW_BYTES = TabCfg<H>::ROW_BYTES;
-    constexpr int WIN_TABLE_BYTES = TabCfg<H>::BYTES;
+    constexpr int TAB_ROW_BYTES = TabCfg<H, FMA>::ROW_BYTES;
+    constexpr int TAB_ENTRY = TabCfg<H, FMA>::ENTRY;
+    constexpr int WIN_TABLE_BYTES = TabCfg<H, FMA>::BYTES;
     float4 *s_a = reinterpret_cast<float4 *>(smem + WIN_TABLE_BYTES);
-    const int pitch = WinSmem<H, TW>::pitch(P.spp);
+    const int pitch = WinSmem<H, TW, FMA>::pitch(P.spp);
     RB *s_b = reinterpret_cast<RB *>(smem + WIN_TABLE_BYTES + (size_t)NPX * pitch * 16);
 
     const int tid = threadIdx.x;
@@ -256,13 +265,13 @@ __global__ void __launch_bounds__(TW) splat_window_kernel(SplatParams P) {
     for (int i = tid; i < 17 * 17; i += TW) {
         const int ty = i / 17, tx = i - ty * 17;
         const float w = (ty < 16 && tx < 16) ? P.table[ty * 16 + tx] : 0.f;
-        *reinterpret_cast<float2 *>(smem + ty * TAB_ROW_BYTES + tx * 8) = make_float2(w, w);
+        if (FMA) *reinterpret_cast<float2 *>(smem + ty * TAB_ROW_BYTES + tx * 8) = make_float2(w, w);
+        else *reinterpret_cast<float *>(smem + ty * TAB_ROW_BYTES + tx * 4) = w;
     }
     // shared-window address of the table, kept opaque so it lives in a register instead of being
     // rematerialised (S2UR/ULEA) at every use
     unsigned tab_base = (unsigned)__cvta_generic_to_shared(smem);
     asm volatile("mov.u32 %0, %0;" : "+r"(tab_base));
-    const u64 negzero = ((u64)P.negzero_bits << 32) | P.negzero_bits;
 
     const int cx0 = P.tb.x0 + blockIdx.x * TW;             // first output column of the strip
     const int cy0 = P.tb.y0 + blockIdx.y * P.rows_per_cta; // first output row
@@ -354,10 +363,11 @@ __global__ void __launch_bounds__(TW) splat_window_kernel(SplatParams P) {
             }
             // ---------------- gather: this thread's column against the row ----------------
             if (col_ok) {
-#pragma unroll
-                for (int d = -H; d <= H; ++d) {
+                // EDGE = -1 / +1: the outermost columns, whose samples may not reach this pixel; 0: interior
+                auto visit = [&](const int d, auto edge_tag) {
+                    constexpr int EDGE = decltype(edge_tag)::value;
                     const int nx = x + d;
-                    if (nx < P.sb.x0 || nx >= P.sb.x1) continue;
+                    if (nx < P.sb.x0 || nx >= P.sb.x1) return;
                     const int pl = nx - (cx0 - H);
                     const float4 *pa = s_a + pl * pitch;
                     const RB *pb = s_b + pl * pitch;
@@ -371,32 +381,37 @@ __global__ void __launch_bounds__(TW) splat_window_kernel(SplatParams P) {
                         // s of neighbouring pixels, which for stratified streams sit in the same stratum and
                         // agree: vote and skip the sample for the whole warp when no lane needs it; a lane
                         // that does not need it reads the zero column.
-                        if (d == H || d == -H) {
-                            const bool reach = d == H ? fx >= pdx - P.rx : fx <= pdx + P.rx;
+                        if (EDGE != 0) {
+                            const bool reach = EDGE > 0 ? fx >= pdx - P.rx : fx <= pdx + P.rx;
                             if (!__any_sync(__activemask(), reach)) continue;
                             ifx = reach ? ifx : TAB_ZERO;
                         }
-                        const unsigned xcol = tab_base + (ifx << 3);  // shared address of table column ifx
+                        const unsigned xcol = tab_base + ifx * TAB_ENTRY;  // shared address of table column ifx
                         const u64 Lrg = pack2(a.x, a.y);
                         const u64 Lb1 = pack2(a.z, 1.f);
 #pragma unroll
                         for (int j = 0; j < ROWS; ++j) {
                             // row byte j times the table's row pitch, plus the column address, in one dot-product
                             // instruction: dp4a(bytes, pitch in byte lane j, xcol)
-                            const u64 ww = lds_pair(__dp4a(rb_word(yb, j >> 2), (unsigned)TAB_ROW_BYTES << (8 * (j & 3)), xcol));
-                            acc_rg[j] = accumulate<FMA>(acc_rg[j], Lrg, ww, negzero);
+                            const unsigned waddr = __dp4a(rb_word(yb, j >> 2), (unsigned)TAB_ROW_BYTES << (8 * (j & 3)), xcol);
                             if (FMA) {
+                                const u64 ww = lds_pair(waddr);
+                                acc_rg[j] = fma2(Lrg, ww, acc_rg[j]);
                                 acc_bw[j] = fma2(Lb1, ww, acc_bw[j]);
                             } else {
-                                // (b*w, w): the product overwrites the low half of the loaded (w, w) pair in place,
-                                // so no (b, 1) operand has to be rebuilt per row
-                                float w0, w1;
-                                unpack2(ww, w0, w1);
-                                acc_bw[j] = add2(acc_bw[j], pack2(a.z * w0, w1));
+                                // products by scalar multiplies (rounded like the CPU's), sums packed: (r*w, g*w) and (b*w, w)
+                                const float w = lds_f32(waddr);
+                                acc_rg[j] = add2(acc_rg[j], pack2(a.x * w, a.y * w));
+                                acc_bw[j] = add2(acc_bw[j], pack2(a.z * w, w));
                             }
                         }
                     }
-                }
+                };
+                // columns are visited left to right: the accumulation order of the oracle (and the reference's add_sample)
+                visit(-H, std::integral_constant<int, -1>{});
+#pragma unroll kWinInteriorUnroll
+                for (int d = -H + 1; d <= H - 1; ++d) visit(d, std::integral_constant<int, 0>{});
+                visit(H, std::integral_constant<int, 1>{});
             }
         }
         // output row ny - H is complete: no later sample row reaches it
@@ -496,7 +511,7 @@ static int env_int(const char *name, int dflt) {
 template <int H, int TW, bool FMA>
 static int launch_window(const SplatParams &P0) {
     SplatParams P = P0;
-    const size_t smem = WinSmem<H, TW>::bytes(P.spp);
+    const size_t smem = WinSmem<H, TW, FMA>::bytes(P.spp);
     static bool attr_set = false;
     if (!attr_set) {
         PB_CUDA(cudaFuncSetAttribute(splat_window_kernel<H, TW, FMA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -529,9 +544,9 @@ static int pick_width(const SplatParams &P) {
     if (force == 128) return launch_window<H, 128, FMA>(P);
     if (force == 64) return launch_window<H, 64, FMA>(P);
     if (force == 32) return launch_window<H, 32, FMA>(P);
-    if (WinSmem<H, 128>::bytes(P.spp) * 2 <= 227 * 1024) return launch_window<H, 128, FMA>(P);
-    if (WinSmem<H, 64>::bytes(P.spp) * 2 <= 227 * 1024) return launch_window<H, 64, FMA>(P);
-    if (WinSmem<H, 32>::bytes(P.spp) <= 227 * 1024) return launch_window<H, 32, FMA>(P);
+    if (WinSmem<H, 128, FMA>::bytes(P.spp) * 2 <= 227 * 1024) return launch_window<H, 128, FMA>(P);
+    if (WinSmem<H, 64, FMA>::bytes(P.spp) * 2 <= 227 * 1024) return launch_window<H, 64, FMA>(P);
+    if (WinSmem<H, 32, FMA>::bytes(P.spp) <= 227 * 1024) return launch_window<H, 32, FMA>(P);
     return -1;
 }
 
@@ -552,7 +567,7 @@ template <int H, bool FMA>
 static int launch_window_batched(const SplatParams &P0, int ntiles, int max_w, int max_h) {
     constexpr int TW = 32;  // renderer tiles are small (16x16 samples -> 20x20 pixels at r = 2)
     SplatParams P = P0;
-    const size_t smem = WinSmem<H, TW>::bytes(P.spp);
+    const size_t smem = WinSmem<H, TW, FMA>::bytes(P.spp);
     if (smem > 227 * 1024) return -1;
     static bool attr_set = false;
     if (!attr_set) {
@@ -587,7 +602,6 @@ int launch_splat_tiles(PbrtFilm *f, int ntiles, const SplatTile *d_tiles, int ma
     P.film = f->d_xyzw;
     P.err = f->d_err;
     P.rows_per_cta = 0;
-    P.negzero_bits = 0x80000000u;
     P.tiles = d_tiles;
     P.tile_out = tile_out;
     const int hx = (int)floorf(P.rx + 0.5f), hy = (int)floorf(P.ry + 0.5f);
@@ -617,7 +631,6 @@ int launch_splat_tile(PbrtFilm *f, const Bounds &sb, const Bounds &tb, int spp, 
     P.film = f->d_xyzw;
     P.err = f->d_err;
     P.rows_per_cta = 0;
-    P.negzero_bits = 0x80000000u;
     P.tiles = nullptr;
     P.tile_out = nullptr;
     if (!(P.rx > 0.f) || !(P.ry > 0.f) || P.rx > 1024.f || P.ry > 1024.f)

@@ -43,9 +43,9 @@ def test_library_is_sm100a_only(pb):
 
 def test_exact_splat_kernel_has_no_fused_accumulate(pb):
     """ptxas fuses f32x2 mul+add into one FFMA2 even with --fmad=false (one rounding instead of two).
-    The exact kernel therefore forms products as fma(L, w, -0) with -0 in a register ptxas cannot see,
-    and adds separately: every FFMA2 in it must take that scalar register (".F32") as its addend, and
-    every product must be followed by a packed add."""
+    The exact kernel therefore forms its products with scalar multiplies and only the sums are packed:
+    it must contain packed adds, and any FFMA2 left in it must take a scalar ".F32" register addend
+    (the -0 trick), never an accumulator."""
     from pbrt_b200 import _lib
 
     sass = subprocess.run(["cuobjdump", "-sass", str(_lib.LIB_PATH)], capture_output=True, text=True).stdout
@@ -58,7 +58,8 @@ def test_exact_splat_kernel_has_no_fused_accumulate(pb):
         ffma2 = re.findall(r"FFMA2 [^;]*;", b)
         fadd2 = re.findall(r"FADD2 [^;]*;", b)
         if "Lb0E" in name:  # exact
-            assert ffma2 and len(fadd2) >= len(ffma2), name
+            assert fadd2 and len(fadd2) >= len(ffma2), name
+            assert len(re.findall(r"FMUL [^;]*;", b)) >= len(fadd2), name
             for ins in ffma2:
                 assert re.search(r", U?R\d+\.F32 ;$", ins), f"{name}: fused accumulate {ins}"
             checked += 1
