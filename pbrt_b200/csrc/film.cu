@@ -684,71 +684,117 @@ __device__ __forceinline__ void resolve_pixel(float4 p, float sx, float sy, floa
 // src/lib.rs:93-99 + src/core/imageio.rs:66-68: byte = clamp(255 * gamma_correct(v) + .5, 0, 255) as u8.
 // to_byte is monotone in v, so it is fully described by 255 thresholds: kToByteThreshold[k] is the smallest
 // f32 with to_byte >= k under a correctly rounded powf (tools/make_to_byte_table.py, no libm involved).
-// The kernel estimates the byte with the MUFU power approximation and corrects it against the
-// thresholds held in shared memory: exact for every input, no slow path, no f64.
+// The kernel needs no power function at all: the top bits of v (exponent + 7 mantissa bits, "slice") index a
+// byte table holding to_byte of the slice's first value; a slice is narrow enough to contain at most one
+// threshold (tests/test_host.py checks that on the table), so one comparison against the next threshold
+// finishes the job.  Exact for every input, no slow path, no branch.
 __device__ const unsigned kToByteThreshold[256] = {
 #include "to_byte_table.inc"
 };
+constexpr unsigned SLICE_SHIFT = 16;                      // 7 mantissa bits per slice
+constexpr unsigned SLICE_FIRST_BITS = 0x39000000u;        // 2^-13 < threshold[1]
+constexpr int SLICE_COUNT = ((0x3f800000u - SLICE_FIRST_BITS) >> SLICE_SHIFT) + 1;  // up to and including 1.0
+constexpr int SLICE_WORDS = (SLICE_COUNT + 3) / 4;
+__device__ unsigned kToByteSlice[SLICE_WORDS];            // filled once by to_byte_slices_kernel
 
-__device__ __forceinline__ unsigned char to_byte(float v, const float *thr) {
-    if (!(v >= thr[1])) return 0;  // below the first threshold, negative, or NaN (`as u8` maps NaN to 0)
-    const float g = v <= 0.0031308f ? 12.92f * v : 1.055f * __powf(v, 1.f / 2.4f) - 0.055f;
-    // the MUFU estimate of 255*g + .5 is within 1e-3 of the exactly rounded value, so its floor is off by
-    // at most one: one step up and one step down against the thresholds settle it without a branch
-    int k = (int)fminf(fmaxf(255.f * g + 0.5f, 1.f), 255.f);
-    k += (k < 255) & (v >= thr[min(k + 1, 255)]);
-    k -= v < thr[k];  // thr[1] <= v, so k stays >= 1
-    return (unsigned char)k;
+__global__ void to_byte_slices_kernel() {
+    unsigned char *out = reinterpret_cast<unsigned char *>(kToByteSlice);
+    for (int i = threadIdx.x; i < SLICE_WORDS * 4; i += blockDim.x) {
+        const unsigned start = SLICE_FIRST_BITS + ((unsigned)min(i, SLICE_COUNT - 1) << SLICE_SHIFT);
+        int k = 0;  // number of thresholds <= start (positive floats order like their bit patterns)
+        for (int step = 128; step > 0; step >>= 1)
+            if (k + step <= 255 && kToByteThreshold[k + step] <= start) k += step;
+        out[i] = (unsigned char)k;
+    }
 }
 
-constexpr int RES_PIX = 256;  // pixels per block; 256*12 B = 3072 B, a multiple of 16
+// thr = [unused, thresholds 1..255, NaN...]: index 256 never steps up
+constexpr int THR_WORDS = 260;
+__device__ __forceinline__ void load_to_byte_tables(float *s_thr, unsigned *s_slice, int tid, int nthreads) {
+    for (int i = tid; i < THR_WORDS; i += nthreads)
+        s_thr[i] = __uint_as_float(i < 256 ? kToByteThreshold[i] : 0x7fc00000u);
+    for (int i = tid; i < SLICE_WORDS; i += nthreads) s_slice[i] = kToByteSlice[i];
+}
 
-template <bool BYTES>
-__global__ void __launch_bounds__(RES_PIX) resolve_kernel(const float4 *__restrict__ xyzw,
-                                                          const float *__restrict__ splat, long long npix,
-                                                          float splat_scale, float scale, void *__restrict__ out) {
-    __shared__ __align__(16) float s_in[RES_PIX * 3];
-    __shared__ __align__(16) float s_out[RES_PIX * 3];
-    __shared__ float s_thr[BYTES ? 256 : 1];
-    const long long base = (long long)blockIdx.x * RES_PIX;
-    const int n = (int)min((long long)RES_PIX, npix - base);
+// src/lib.rs:93-99 + src/core/imageio.rs:66-68: byte = clamp(255 * gamma_correct(v) + .5, 0, 255) as u8
+__device__ __forceinline__ unsigned to_byte(float v, const float *thr, const unsigned *slice) {
+    // below 2^-13 (also negative, and NaN: `as u8` maps NaN to 0) every input gives 0, above 1.0 every input 255
+    const float vc = fminf(fmaxf(v, 1.220703125e-4f), 1.f);
+    const unsigned idx = (__float_as_uint(vc) >> SLICE_SHIFT) - (SLICE_FIRST_BITS >> SLICE_SHIFT);
+    const unsigned k0 = reinterpret_cast<const unsigned char *>(slice)[idx];
+    return k0 + (vc >= thr[k0 + 1]);
+}
+
+constexpr int RES_PIX = 256;  // resolve_to_frames_kernel: pixels per block; 256*12 B = 3072 B, a multiple of 16
+constexpr int RES_THREADS = 256;
+
+// PPT pixels per thread, pixel j of thread t = base + j*RES_THREADS + t: coalesced float4 loads, PPT of them in flight.
+template <bool BYTES, int PPT>
+__global__ void __launch_bounds__(RES_THREADS) resolve_kernel(const float4 *__restrict__ xyzw,
+                                                              const float *__restrict__ splat, long long npix,
+                                                              float splat_scale, float scale, void *__restrict__ out) {
+    constexpr int TILE = RES_THREADS * PPT;
+    __shared__ __align__(16) float s_in[TILE * 3];
+    __shared__ __align__(16) float s_out[BYTES ? TILE * 3 / 4 : TILE * 3];
+    __shared__ float s_thr[BYTES ? THR_WORDS : 1];
+    __shared__ unsigned s_slice[BYTES ? SLICE_WORDS : 1];
+    const long long base = (long long)blockIdx.x * TILE;
+    const int n = (int)min((long long)TILE, npix - base);
     const int tid = threadIdx.x;
-    if (BYTES) s_thr[tid] = __uint_as_float(kToByteThreshold[tid]);  // RES_PIX == 256 threads
-    // 28 B / pixel in: float4 xyzw straight to a register, splat through shared memory
-    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (tid < n) p = pb::ldg_stream(&xyzw[base + tid]);
-    if (n == RES_PIX) {
-        const float4 *src = reinterpret_cast<const float4 *>(splat + base * 3);
-        if (tid < RES_PIX * 3 / 4) reinterpret_cast<float4 *>(s_in)[tid] = pb::ldg_stream(&src[tid]);
-    } else {
-        for (int i = tid; i < n * 3; i += RES_PIX) s_in[i] = splat[base * 3 + i];
+    const bool full = n == TILE;
+    // 28 B / pixel in: float4 xyzw straight to registers, splat through shared memory
+    float4 p[PPT];
+#pragma unroll
+    for (int j = 0; j < PPT; ++j) {
+        p[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (full || j * RES_THREADS + tid < n) p[j] = pb::ldg_stream(&xyzw[base + j * RES_THREADS + tid]);
     }
+    if (full) {
+        const float4 *src = reinterpret_cast<const float4 *>(splat + base * 3);
+#pragma unroll
+        for (int i = 0; i < (TILE * 3 / 4 + RES_THREADS - 1) / RES_THREADS; ++i)
+            if (i * RES_THREADS + tid < TILE * 3 / 4)
+                reinterpret_cast<float4 *>(s_in)[i * RES_THREADS + tid] = pb::ldg_stream(&src[i * RES_THREADS + tid]);
+    } else {
+        for (int i = tid; i < n * 3; i += RES_THREADS) s_in[i] = splat[base * 3 + i];
+    }
+    if (BYTES) load_to_byte_tables(s_thr, s_slice, tid, RES_THREADS);
     __syncthreads();
-    if (tid < n) {
-        float r, g, b;
-        resolve_pixel(p, s_in[3 * tid], s_in[3 * tid + 1], s_in[3 * tid + 2], splat_scale, scale, r, g, b);
-        if (BYTES) {
-            unsigned char *o = reinterpret_cast<unsigned char *>(s_out);
-            o[3 * tid] = to_byte(r, s_thr); o[3 * tid + 1] = to_byte(g, s_thr); o[3 * tid + 2] = to_byte(b, s_thr);
-        } else {
-            s_out[3 * tid] = r; s_out[3 * tid + 1] = g; s_out[3 * tid + 2] = b;
+#pragma unroll
+    for (int j = 0; j < PPT; ++j) {
+        const int q = j * RES_THREADS + tid;
+        if (full || q < n) {
+            float r, g, b;
+            resolve_pixel(p[j], s_in[3 * q], s_in[3 * q + 1], s_in[3 * q + 2], splat_scale, scale, r, g, b);
+            if (BYTES) {
+                unsigned char *o = reinterpret_cast<unsigned char *>(s_out);
+                o[3 * q] = (unsigned char)to_byte(r, s_thr, s_slice);
+                o[3 * q + 1] = (unsigned char)to_byte(g, s_thr, s_slice);
+                o[3 * q + 2] = (unsigned char)to_byte(b, s_thr, s_slice);
+            } else {
+                s_out[3 * q] = r; s_out[3 * q + 1] = g; s_out[3 * q + 2] = b;
+            }
         }
     }
     __syncthreads();
     if (BYTES) {
         unsigned char *dst = reinterpret_cast<unsigned char *>(out) + base * 3;
-        if (n == RES_PIX) {
-            if (tid < RES_PIX * 3 / 16) reinterpret_cast<uint4 *>(dst)[tid] = reinterpret_cast<uint4 *>(s_out)[tid];
+        if (full) {
+            if (tid < TILE * 3 / 16) reinterpret_cast<uint4 *>(dst)[tid] = reinterpret_cast<uint4 *>(s_out)[tid];
         } else {
             const unsigned char *o = reinterpret_cast<const unsigned char *>(s_out);
-            for (int i = tid; i < n * 3; i += RES_PIX) dst[i] = o[i];
+            for (int i = tid; i < n * 3; i += RES_THREADS) dst[i] = o[i];
         }
     } else {
         float *dst = reinterpret_cast<float *>(out) + base * 3;
-        if (n == RES_PIX) {
-            if (tid < RES_PIX * 3 / 4) pb::stg_stream(&reinterpret_cast<float4 *>(dst)[tid], reinterpret_cast<float4 *>(s_out)[tid]);
+        if (full) {
+#pragma unroll
+            for (int i = 0; i < (TILE * 3 / 4 + RES_THREADS - 1) / RES_THREADS; ++i)
+                if (i * RES_THREADS + tid < TILE * 3 / 4)
+                    pb::stg_stream(&reinterpret_cast<float4 *>(dst)[i * RES_THREADS + tid],
+                                   reinterpret_cast<float4 *>(s_out)[i * RES_THREADS + tid]);
         } else {
-            for (int i = tid; i < n * 3; i += RES_PIX) dst[i] = s_out[i];
+            for (int i = tid; i < n * 3; i += RES_THREADS) dst[i] = s_out[i];
         }
     }
 }
@@ -765,9 +811,19 @@ static int resolve_impl(const PbrtFilm *f, float splat_scale, void *out, int dst
     } else if (((uintptr_t)out & 15) != 0) {
         return fail(PBRT_E_INVALID, "device output must be 16-byte aligned");
     }
-    int blocks = (int)((f->npix + RES_PIX - 1) / RES_PIX);
-    resolve_kernel<BYTES><<<blocks, RES_PIX, 0, ctx().stream>>>(f->d_xyzw, f->d_splat, (long long)f->npix,
-                                                                splat_scale, f->scale, d_out);
+    if (BYTES) {
+        static bool slices_ready = false;  // one device per process (pbrt_b200_init)
+        if (!slices_ready) {
+            to_byte_slices_kernel<<<1, 256, 0, ctx().stream>>>();
+            PB_LAUNCH_CHECK("to_byte_slices_kernel");
+            slices_ready = true;
+        }
+    }
+    static int ppt_env = getenv("PBRT_B200_RES_PPT") ? atoi(getenv("PBRT_B200_RES_PPT")) : 0;
+    const int PPT = ppt_env ? ppt_env : (BYTES ? 4 : 2);
+    int blocks = (int)((f->npix + RES_THREADS * PPT - 1) / (RES_THREADS * PPT));
+#define RES_LAUNCH(N) resolve_kernel<BYTES, N><<<blocks, RES_THREADS, 0, ctx().stream>>>(f->d_xyzw, f->d_splat, (long long)f->npix, splat_scale, f->scale, d_out)
+    if (PPT == 1) RES_LAUNCH(1); else if (PPT == 2) RES_LAUNCH(2); else if (PPT == 8) RES_LAUNCH(8); else RES_LAUNCH(4);
     PB_LAUNCH_CHECK("resolve_kernel");
     if (to_host) {
         PB_CUDA(cudaMemcpyAsync(out, d_out, bytes, cudaMemcpyDeviceToHost, ctx().stream));

@@ -110,3 +110,23 @@ def test_to_byte_threshold_table_agrees_with_glibc(orc):
         below = struct.unpack("<f", struct.pack("<I", thr[k] - 1))[0]
         assert orc.orc_to_byte(v) == k, (k, v)
         assert orc.orc_to_byte(below) == k - 1, (k, below)
+
+
+def test_to_byte_slices_hold_at_most_one_threshold():
+    """The resolve kernel looks to_byte up by the top bits of the float (exponent + 6 mantissa bits, a "slice")
+    and settles the result with ONE comparison against the next threshold.  That is exact only if no slice
+    contains two thresholds and the range below the first slice / above the last maps to 0 / 255."""
+    import re
+    from pathlib import Path
+
+    txt = (Path(__file__).resolve().parent.parent / "pbrt_b200" / "csrc" / "to_byte_table.inc").read_text()
+    thr = [int(h, 16) for h in re.findall(r"0x([0-9a-f]{8})u", txt)][1:]
+    cu = (Path(__file__).resolve().parent.parent / "pbrt_b200" / "csrc" / "film.cu").read_text()
+    shift = int(re.search(r"SLICE_SHIFT = (\d+);", cu).group(1))
+    first = int(re.search(r"SLICE_FIRST_BITS = 0x([0-9a-f]+)u;", cu).group(1), 16)
+    one = 0x3F800000
+    assert first < thr[0], "inputs below the first slice must all map to byte 0"
+    assert thr[-1] <= one, "1.0 must already map to 255"
+    for start in range(first, one, 1 << shift):
+        inside = [t for t in thr if start < t < start + (1 << shift)]
+        assert len(inside) <= 1, (hex(start), inside)
