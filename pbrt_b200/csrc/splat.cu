@@ -134,6 +134,10 @@ __global__ void __launch_bounds__(256) splat_gather_generic_kernel(SplatParams P
 #ifndef PBRT_WIN_UNROLL
 #define PBRT_WIN_UNROLL 8
 #endif
+#ifndef PBRT_PREPASS_BATCH
+#define PBRT_PREPASS_BATCH 4
+#endif
+constexpr int kPrepassBatch = PBRT_PREPASS_BATCH;
 constexpr int kWinUnroll = PBRT_WIN_UNROLL;
 #ifndef PBRT_WIN_INTERIOR_UNROLL
 #define PBRT_WIN_INTERIOR_UNROLL 1
@@ -297,6 +301,9 @@ __global__ void __launch_bounds__(TW) splat_window_kernel(SplatParams P) {
     u64 acc_rg[ROWS], acc_bw[ROWS];
 #pragma unroll
     for (int j = 0; j < ROWS; ++j) acc_rg[j] = acc_bw[j] = 0ull;
+    unsigned errbits = 0;  // contract violations seen by this thread; reported once at the end
+    // lanes that gather (the last strip of a row may be narrower than the CTA)
+    const unsigned gather_mask = __ballot_sync(0xffffffffu, col_ok);
 
     for (int ny = cy0 - H; ny < cy1 + H; ++ny) {
         const bool row_has_samples = ny >= P.sb.y0 && ny < P.sb.y1 && nstaged > 0;
@@ -308,7 +315,7 @@ __global__ void __launch_bounds__(TW) splat_window_kernel(SplatParams P) {
             const float4 *grgbw = P.rgbw + row_base;
             const float fny = (float)ny;
             int q = q0, sidx = r0;
-            constexpr int U = 4;  // samples per thread per trip: all loads issued before any is consumed
+            constexpr int U = kPrepassBatch;  // samples per thread per trip: all loads issued before any is consumed
             for (int e0 = tid; e0 < nstaged; e0 += U * TW) {
                 float2 p[U];
                 float4 L[U];
@@ -327,8 +334,8 @@ __global__ void __launch_bounds__(TW) splat_window_kernel(SplatParams P) {
                         const float cr = L[u].x * L[u].w, cg = L[u].y * L[u].w, cb = L[u].z * L[u].w;
                         // contract: the sample lies in its nominal pixel (closed) and its radiance is finite
                         if (!(p[u].x >= fnx && p[u].x <= fnx + 1.f && p[u].y >= fny && p[u].y <= fny + 1.f))
-                            atomicOr(P.err, ERRBIT_NOT_PIXEL_MAJOR);
-                        if (!(fabsf(cr) + fabsf(cg) + fabsf(cb) < inf)) atomicOr(P.err, ERRBIT_NONFINITE);
+                            errbits |= ERRBIT_NOT_PIXEL_MAJOR;
+                        if (!(fabsf(cr) + fabsf(cg) + fabsf(cb) < inf)) errbits |= ERRBIT_NONFINITE;
                         const float pdx = p[u].x - 0.5f, pdy = p[u].y - 0.5f;
                         unsigned bits[12];
 #pragma unroll
@@ -367,25 +374,15 @@ __global__ void __launch_bounds__(TW) splat_window_kernel(SplatParams P) {
                 auto visit = [&](const int d, auto edge_tag) {
                     constexpr int EDGE = decltype(edge_tag)::value;
                     const int nx = x + d;
-                    if (nx < P.sb.x0 || nx >= P.sb.x1) return;
+                    const bool in_range = nx >= P.sb.x0 && nx < P.sb.x1;
+                    // lanes that take part in this visit's votes (columns at the film edge drop out)
+                    const unsigned visit_mask = __ballot_sync(gather_mask, in_range);
+                    if (!in_range) return;
                     const int pl = nx - (cx0 - H);
                     const float4 *pa = s_a + pl * pitch;
                     const RB *pb = s_b + pl * pitch;
-#pragma unroll kWinUnroll
-                    for (int s = 0; s < spp; ++s) {
-                        const float4 a = pa[s];
-                        const RB yb = pb[s];
-                        const float pdx = a.w;
-                        unsigned ifx = bin_bits((fx - pdx) * irx16) & 0xFu;
-                        // Outermost columns: x must lie in [ceil(pdx - r), floor(pdx + r)].  Lanes hold sample
-                        // s of neighbouring pixels, which for stratified streams sit in the same stratum and
-                        // agree: vote and skip the sample for the whole warp when no lane needs it; a lane
-                        // that does not need it reads the zero column.
-                        if (EDGE != 0) {
-                            const bool reach = EDGE > 0 ? fx >= pdx - P.rx : fx <= pdx + P.rx;
-                            if (!__any_sync(__activemask(), reach)) continue;
-                            ifx = reach ? ifx : TAB_ZERO;
-                        }
+                    // all window rows of one sample against this column; ifx = table column (TAB_ZERO adds exact zeros)
+                    auto taps = [&](const float4 a, const RB yb, const unsigned ifx) {
                         const unsigned xcol = tab_base + ifx * TAB_ENTRY;  // shared address of table column ifx
                         const u64 Lrg = pack2(a.x, a.y);
                         const u64 Lb1 = pack2(a.z, 1.f);
@@ -404,6 +401,25 @@ __global__ void __launch_bounds__(TW) splat_window_kernel(SplatParams P) {
                                 acc_rg[j] = add2(acc_rg[j], pack2(a.x * w, a.y * w));
                                 acc_bw[j] = add2(acc_bw[j], pack2(a.z * w, w));
                             }
+                        }
+                    };
+                    if (EDGE == 0) {
+#pragma unroll kWinUnroll
+                        for (int s = 0; s < spp; ++s) {
+                            const float4 a = pa[s];
+                            taps(a, pb[s], bin_bits((fx - a.w) * irx16) & 0xFu);
+                        }
+                    } else {
+                        // Outermost columns: x must lie in [ceil(pdx - r), floor(pdx + r)].  Lanes hold sample s of
+                        // neighbouring pixels, which for stratified streams sit in the same stratum and agree: vote
+                        // and skip the sample for the whole warp when no lane needs it; a lane that does not need
+                        // it reads the zero column.
+#pragma unroll kWinUnroll
+                        for (int s = 0; s < spp; ++s) {
+                            const float4 a = pa[s];
+                            const bool reach = EDGE > 0 ? fx >= a.w - P.rx : fx <= a.w + P.rx;
+                            if (!__any_sync(visit_mask, reach)) continue;
+                            taps(a, pb[s], reach ? bin_bits((fx - a.w) * irx16) & 0xFu : (unsigned)TAB_ZERO);
                         }
                     }
                 };
@@ -429,6 +445,7 @@ __global__ void __launch_bounds__(TW) splat_window_kernel(SplatParams P) {
         for (int j = 0; j + 1 < ROWS; ++j) { acc_rg[j] = acc_rg[j + 1]; acc_bw[j] = acc_bw[j + 1]; }
         acc_rg[ROWS - 1] = acc_bw[ROWS - 1] = 0ull;
     }
+    if (errbits) atomicOr(P.err, (int)errbits);
 }
 
 // ---- scatter with shared-memory atomics --------------------------------------------------
