@@ -23,6 +23,9 @@
  *     pbrt_b200_synchronize().
  *   - work is ordered on one stream per process (pbrt_b200_set_stream); calls that return data
  *     to the host synchronise that stream, the others are asynchronous.
+ *   - compute entry points may be called from several host threads at once (FilmTile is Send: workers
+ *     merge their own tiles); each call takes one process-wide lock, as the reference takes its pixel
+ *     Mutex (src/core/film.rs:73, :316), so concurrent calls are serialised in arrival order.
  *   - there is no CPU fallback: every compute entry point fails with PBRT_E_CUDA when no
  *     sm_100 device is usable.
  *

@@ -38,6 +38,11 @@ int cuda_fail(cudaError_t e, const char *what) {
 }
 
 static std::mutex g_init_mu;
+// One lock for every compute entry point: the reference serialises all pixel access through one Mutex
+// (film.rs:73) and FilmTile is Send, so worker threads may call merge_film_tile concurrently.  Handles carry
+// mutable host-side state (staging buffers, cached tile index) and all work goes to one stream anyway.
+static std::recursive_mutex g_api_mu;
+#define PB_API_LOCK std::lock_guard<std::recursive_mutex> pb_api_lock_(pb::g_api_mu)
 
 int ensure_ready() {
     if (ctx().ready) return PBRT_OK;
@@ -121,12 +126,14 @@ extern "C" int pbrt_b200_init(int device) {
 }
 
 extern "C" int pbrt_b200_set_stream(void *s) {
+    PB_API_LOCK;
     if (int rc = pb::ensure_ready()) return rc;
     ctx().stream = s ? (cudaStream_t)s : ctx().own_stream;
     return PBRT_OK;
 }
 
 extern "C" int pbrt_b200_synchronize(void) {
+    PB_API_LOCK;
     if (int rc = pb::ensure_ready()) return rc;
     PB_CUDA(cudaStreamSynchronize(ctx().copy_stream));
     PB_CUDA(cudaStreamSynchronize(ctx().stream));
@@ -370,6 +377,7 @@ extern "C" int pbrt_film_create_sharded(int32_t xres, int32_t yres, const float 
 }
 
 extern "C" int pbrt_film_destroy(PbrtFilm *f) {
+    PB_API_LOCK;
     if (!f) return PBRT_OK;
     if (ctx().ready) { cudaStreamSynchronize(ctx().copy_stream); cudaStreamSynchronize(ctx().stream); }
     cudaFree(f->d_xyzw);
@@ -540,6 +548,7 @@ static bool inside(const Bounds &outer, const Bounds &b) {
 }
 
 extern "C" int pbrt_film_merge_tile(PbrtFilm *f, const int32_t tbv[4], const float *rgbw, int src_is_device) {
+    PB_API_LOCK;
     if (!f || !tbv) return fail(PBRT_E_INVALID, "null argument");
     Bounds tb{tbv[0], tbv[1], tbv[2], tbv[3]};
     // Bounds2i::iter over an inverted or empty box yields nothing (bounds.rs:284-288)
@@ -563,6 +572,7 @@ extern "C" int pbrt_film_merge_tile(PbrtFilm *f, const int32_t tbv[4], const flo
 
 extern "C" int pbrt_film_merge_tiles(PbrtFilm *f, int32_t ntiles, const int32_t *tbs, const int64_t *offsets,
                                      const float *rgbw, int64_t total_pixels, int src_is_device) {
+    PB_API_LOCK;
     if (!f) return fail(PBRT_E_INVALID, "null film");
     if (ntiles <= 0) return PBRT_OK;
     if (!tbs || !offsets || !rgbw) return fail(PBRT_E_INVALID, "null argument");
@@ -834,9 +844,11 @@ static int resolve_impl(const PbrtFilm *f, float splat_scale, void *out, int dst
 }
 
 extern "C" int pbrt_film_resolve_rgb(const PbrtFilm *f, float splat_scale, float *out, int dst_is_device) {
+    PB_API_LOCK;
     return resolve_impl<false>(f, splat_scale, out, dst_is_device);
 }
 extern "C" int pbrt_film_resolve_rgb8(const PbrtFilm *f, float splat_scale, uint8_t *out, int dst_is_device) {
+    PB_API_LOCK;
     return resolve_impl<true>(f, splat_scale, out, dst_is_device);
 }
 
@@ -884,6 +896,7 @@ __global__ void __launch_bounds__(RES_PIX) resolve_to_frames_kernel(const float4
 }
 
 extern "C" int pbrt_film_resolve_rgb_to_frames(const PbrtFilm *f, float splat_scale, int32_t nframes, void *const *frames) {
+    PB_API_LOCK;
     if (!f || !frames) return fail(PBRT_E_INVALID, "null argument");
     if (nframes < 1 || nframes > MAX_FRAMES) return fail(PBRT_E_INVALID, "between 1 and %d frames", MAX_FRAMES);
     if (f->npix == 0) return PBRT_OK;
@@ -904,6 +917,7 @@ extern "C" int pbrt_film_resolve_rgb_to_frames(const PbrtFilm *f, float splat_sc
 }
 
 extern "C" int pbrt_film_get_pixel_xyz(const PbrtFilm *f, int32_t x, int32_t y, float out[3]) {
+    PB_API_LOCK;
     if (!f || !out) return fail(PBRT_E_INVALID, "null argument");
     if (x < f->owned.x0 || x >= f->owned.x1 || y < f->owned.y0 || y >= f->owned.y1)
         return fail(PBRT_E_RANGE, "p [%d, %d] outside film", x, y);  // film.rs:391-396
@@ -926,6 +940,7 @@ __global__ void read_pixels_kernel(const float4 *__restrict__ xyzw, const float 
 }
 
 extern "C" int pbrt_film_read_pixels(const PbrtFilm *f, float *out7, int dst_is_device) {
+    PB_API_LOCK;
     if (!f || !out7) return fail(PBRT_E_INVALID, "null argument");
     if (f->npix == 0) return PBRT_OK;
     size_t bytes = (size_t)f->npix * 7 * sizeof(float);
@@ -951,6 +966,7 @@ extern "C" int pbrt_film_device_buffers(const PbrtFilm *f, void **xyzw, void **s
 }
 
 extern "C" int pbrt_film_check(PbrtFilm *f) {
+    PB_API_LOCK;
     if (!f) return fail(PBRT_E_INVALID, "null film");
     int e = 0;
     PB_CUDA(cudaMemcpyAsync(&e, f->d_err, sizeof e, cudaMemcpyDeviceToHost, ctx().stream));
@@ -1008,6 +1024,7 @@ __global__ void __launch_bounds__(256) scatter_samples_kernel(float4 *__restrict
 
 extern "C" int pbrt_film_add_samples(PbrtFilm *f, const int32_t sbv[4], uint64_t n, const float *xy, const float *rgbw,
                                      int src_is_device) {
+    PB_API_LOCK;
     if (!f || !sbv) return fail(PBRT_E_INVALID, "null argument");
     Bounds tb;
     if (int rc = tile_bounds_impl(f, sbv, f->owned, &tb)) return rc;
@@ -1067,6 +1084,7 @@ __global__ void __launch_bounds__(256) add_splats_kernel(float *__restrict__ spl
 }
 
 extern "C" int pbrt_film_add_splats(PbrtFilm *f, uint64_t n, const float *xy, const float *rgb, int src_is_device) {
+    PB_API_LOCK;
     if (!f) return fail(PBRT_E_INVALID, "null film");
     if (n == 0 || f->npix == 0) return PBRT_OK;
     if (!xy || !rgb) return fail(PBRT_E_INVALID, "null argument");
@@ -1095,6 +1113,7 @@ __global__ void __launch_bounds__(256) set_image_kernel(float4 *__restrict__ xyz
 }
 
 extern "C" int pbrt_film_set_image(PbrtFilm *f, const float *rgb, int src_is_device) {
+    PB_API_LOCK;
     if (!f || !rgb) return fail(PBRT_E_INVALID, "null argument");
     if (f->npix == 0) return PBRT_OK;
     const float *d_rgb = rgb;
@@ -1110,6 +1129,7 @@ extern "C" int pbrt_film_set_image(PbrtFilm *f, const float *rgb, int src_is_dev
 
 // [T2] pbrt-v3 Film::Clear
 extern "C" int pbrt_film_clear(PbrtFilm *f) {
+    PB_API_LOCK;
     if (!f) return fail(PBRT_E_INVALID, "null film");
     if (f->npix == 0) return PBRT_OK;
     PB_CUDA(cudaMemsetAsync(f->d_xyzw, 0, (size_t)f->npix * sizeof(float4), ctx().stream));
@@ -1120,6 +1140,7 @@ extern "C" int pbrt_film_clear(PbrtFilm *f) {
 // [T2] the pixel-major splat: bounds on the host, kernels in splat.cu
 extern "C" int pbrt_film_add_samples_tile(PbrtFilm *f, const int32_t sbv[4], int32_t spp, const float *xy,
                                           const float *rgbw, int src_is_device, int mode) {
+    PB_API_LOCK;
     if (!f || !sbv) return fail(PBRT_E_INVALID, "null argument");
     if (spp < 1) return fail(PBRT_E_INVALID, "spp must be >= 1");
     if (mode < PBRT_SPLAT_EXACT || mode > PBRT_SPLAT_ATOMIC) return fail(PBRT_E_INVALID, "unknown splat mode %d", mode);
@@ -1179,6 +1200,7 @@ extern "C" int pbrt_film_add_samples_tile(PbrtFilm *f, const int32_t sbv[4], int
 extern "C" int pbrt_film_add_samples_tiles(PbrtFilm *f, int32_t ntiles, const int32_t *sbs, const int64_t *sample_offsets,
                                            int32_t spp, const float *xy, const float *rgbw, int64_t total_samples,
                                            int src_is_device, int mode) {
+    PB_API_LOCK;
     if (!f) return fail(PBRT_E_INVALID, "null film");
     if (ntiles <= 0) return PBRT_OK;
     if (!sbs || !sample_offsets || !xy || !rgbw) return fail(PBRT_E_INVALID, "null argument");
@@ -1295,6 +1317,7 @@ static int fill_grid(unsigned long long nvec) {
 }
 
 extern "C" int pbrt_texture_constant_eval_f32(float value, uint64_t n, float *out, int dst_is_device) {
+    PB_API_LOCK;
     if (int rc = pb::ensure_ready()) return rc;
     if (n == 0) return PBRT_OK;
     if (!out) return fail(PBRT_E_INVALID, "null output");
@@ -1311,6 +1334,7 @@ extern "C" int pbrt_texture_constant_eval_f32(float value, uint64_t n, float *ou
 }
 
 extern "C" int pbrt_texture_constant_eval_rgb(const float value[3], uint64_t n, float *out, int dst_is_device) {
+    PB_API_LOCK;
     if (int rc = pb::ensure_ready()) return rc;
     if (n == 0) return PBRT_OK;
     if (!out || !value) return fail(PBRT_E_INVALID, "null argument");
@@ -1336,6 +1360,7 @@ __global__ void weight_lut_kernel(float *out) {
 }
 
 extern "C" int pbrt_mipmap_weight_lut(float out[128]) {
+    PB_API_LOCK;
     if (int rc = pb::ensure_ready()) return rc;
     if (!out) return fail(PBRT_E_INVALID, "null output");
     void *d;
@@ -1371,6 +1396,7 @@ __global__ void __launch_bounds__(128) synth_samples_kernel(Bounds b, Bounds ib,
 
 extern "C" int pbrt_synth_samples(const int32_t bv[4], const int32_t ibv[4], int32_t spp, uint64_t seed, float *xy_dev,
                                   float *rgbw_dev) {
+    PB_API_LOCK;
     if (int rc = pb::ensure_ready()) return rc;
     if (!bv || !xy_dev || !rgbw_dev || spp < 1) return fail(PBRT_E_INVALID, "bad argument");
     Bounds b{bv[0], bv[1], bv[2], bv[3]};
@@ -1402,6 +1428,7 @@ __global__ void __launch_bounds__(256) synth_tiles_kernel(int ntiles, const long
 
 extern "C" int pbrt_synth_tiles(int32_t ntiles, const int64_t *offsets, const int64_t *counts, uint64_t seed,
                                 float *rgbw_dev, int64_t total_pixels) {
+    PB_API_LOCK;
     if (int rc = pb::ensure_ready()) return rc;
     if (ntiles <= 0) return PBRT_OK;
     if (!offsets || !counts || !rgbw_dev) return fail(PBRT_E_INVALID, "null argument");

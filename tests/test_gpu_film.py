@@ -292,3 +292,43 @@ def test_merge_and_resolve_special_values_bitwise(gpu, orc):
     got8 = film.resolve_rgb8(0.75).reshape(-1)
     want8 = np.array([orc.orc_to_byte(float(v)) for v in rb.reshape(-1)], dtype=np.uint8)
     assert np.array_equal(got8, want8)
+
+
+def test_merge_film_tile_from_worker_threads(gpu):
+    """FilmTile is Send and the reference serialises pixel access through one Mutex (film.rs:73, :316): worker
+    threads may merge their tiles into one Film concurrently.  The ABI takes a lock per call; host tile buffers
+    go through one per-film staging buffer, so an unlocked race would corrupt tiles.  Integer-valued tiles make
+    the sums independent of the merge order."""
+    import threading
+
+    film = gpu.Film.new([256, 256], [[0, 0], [1, 1]], box8(gpu), 35.0, "t.png", 1.0, 1.0)
+    rng = np.random.default_rng(5)
+    jobs = []
+    want = np.zeros((256, 256, 4), dtype=np.float64)
+    for _ in range(64):
+        x0, y0 = rng.integers(0, 200, size=2)
+        w, h = rng.integers(8, 56, size=2)
+        px = rng.integers(0, 8, size=(h, w, 4)).astype(np.float32)
+        jobs.append(((int(x0), int(y0), int(x0 + w), int(y0 + h)), px))
+        want[y0:y0 + h, x0:x0 + w] += px
+    errors = []
+
+    def worker(chunk):
+        try:
+            for tb, px in chunk:
+                film.merge_tile_raw(tb, px.reshape(-1, 4))
+        except Exception as e:  # noqa: BLE001 - surfaced below
+            errors.append(e)
+
+    threads = [threading.Thread(target=worker, args=(jobs[i::8],)) for i in range(8)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    got = film.read_pixels().reshape(256, 256, 7)
+    # weights: plain sum; xyz: rgb_to_xyz of small integers summed — compare the weight channel exactly and the
+    # colour channels against the oracle matrix applied per tile in float64 (exact for these magnitudes to 1e-4)
+    assert np.array_equal(got[..., 3], want[..., 3].astype(np.float32))
+    m = np.array([[0.412453, 0.357580, 0.180423], [0.212671, 0.715160, 0.072169], [0.019334, 0.119193, 0.950227]])
+    assert np.allclose(got[..., :3], want[..., :3] @ m.T, rtol=1e-5, atol=1e-4)
