@@ -16,7 +16,7 @@
  *     The reference uses isize; a host shim must range-check before narrowing.
  *   - `*_is_device` = 0 (PBRT_MEM_HOST): pointer is host memory, the call copies and, for outputs,
  *     returns when the data has arrived; 1 (PBRT_MEM_DEVICE): pointer is device memory on the film's
- *     device and is used in place; 2 (PBRT_MEM_PINNED_ASYNC, accepted by add_samples_tile and
+ *     device and is used in place; 2 (PBRT_MEM_PINNED_ASYNC, accepted by add_samples_tile[_rgb] and
  *     resolve_rgb / resolve_rgb8): pointer is page-locked host memory and the transfer is only
  *     enqueued — inputs are double-buffered on a copy stream so that the upload of one call overlaps
  *     the kernels of the previous one; the caller keeps the buffers untouched until
@@ -165,6 +165,15 @@ enum { PBRT_SPLAT_EXACT = 0,   /* gather, mul then add: bit-identical to the CPU
        PBRT_SPLAT_ATOMIC = 2 };/* scatter with shared-memory atomics; order not deterministic */
 int pbrt_film_add_samples_tile(PbrtFilm *film, const int32_t sample_bounds[4], int32_t spp, const float *xy,
                                const float *rgbw, int src_is_device, int mode);
+/*
+ * [T2] the same with the radiance as separate streams, the shape of pbrt's AddSample(pFilm, L, sampleWeight)
+ * arguments: rgb = 3 floats per sample, sample_weight = 1 float per sample or NULL for "every weight is 1"
+ * (then nothing is transferred for it: 20 instead of 24 bytes per sample from a host buffer).  The streams
+ * are interleaved on the device and the same kernels run; results are bit-identical to add_samples_tile
+ * with rgbw = {rgb, sample_weight}.
+ */
+int pbrt_film_add_samples_tile_rgb(PbrtFilm *film, const int32_t sample_bounds[4], int32_t spp, const float *xy,
+                                   const float *rgb, const float *sample_weight, int src_is_device, int mode);
 /*
  * [T2] the same for `ntiles` tiles at once, the way a renderer works (pbrt renders 16x16-pixel tiles):
  * tile i has sample bounds sample_bounds[4i..4i+3] and its pixel-major samples start at sample

@@ -78,6 +78,7 @@ PROTOTYPES = {
     "pbrt_film_merge_tile": (C.c_int, [_vp, _i32p, _vp, C.c_int]),
     "pbrt_film_merge_tiles": (C.c_int, [_vp, C.c_int32, _i32p, _i64p, _vp, C.c_int64, C.c_int]),
     "pbrt_film_add_samples_tile": (C.c_int, [_vp, _i32p, C.c_int32, _vp, _vp, C.c_int, C.c_int]),
+    "pbrt_film_add_samples_tile_rgb": (C.c_int, [_vp, _i32p, C.c_int32, _vp, _vp, _vp, C.c_int, C.c_int]),
     "pbrt_film_add_samples_tiles": (C.c_int, [_vp, C.c_int32, _i32p, _i64p, C.c_int32, _vp, _vp, C.c_int64, C.c_int, C.c_int]),
     "pbrt_film_add_samples": (C.c_int, [_vp, _i32p, C.c_uint64, _vp, _vp, C.c_int]),
     "pbrt_film_add_splats": (C.c_int, [_vp, C.c_uint64, _vp, _vp, C.c_int]),

@@ -114,8 +114,8 @@ struct PbrtFilm {
     void *d_tile_desc;       // add_samples_tiles: SplatTile array (grow-only)
     size_t tile_desc_bytes;
     // PBRT_MEM_PINNED_ASYNC inputs: two staging sets filled on the copy stream while the other is consumed
-    void *d_pipe[2][2];      // [set][0 = xy, 1 = rgbw]
-    size_t pipe_bytes[2][2];
+    void *d_pipe[2][4];      // [set][0 = xy, 1 = rgbw, 2 = rgb, 3 = sample weights]
+    size_t pipe_bytes[2][4];
     cudaEvent_t ev_staged[2], ev_consumed[2];
     bool pipe_ready;
     int pipe_turn;

@@ -265,6 +265,23 @@ class Film:
             dev_a = 2  # PBRT_MEM_PINNED_ASYNC
         _lib.check(_lib.lib.pbrt_film_add_samples_tile(self._h, _lib.i32x4(sb.as4()), int(spp), pxy, prgbw, dev_a, int(mode)))
 
+    def add_samples_tile_rgb(self, sample_bounds, spp: int, xy, rgb, sample_weight=None, mode: int = SPLAT_EXACT,
+                             pinned_async: bool = False) -> None:
+        """add_samples_tile with the radiance as separate streams: `rgb` (n, 3) and `sample_weight` (n,) or None
+        for all-ones (then no weight stream is transferred).  Bit-identical to the interleaved form."""
+        sb = Bounds2i.of(sample_bounds)
+        pxy, dev_a, k1 = as_pointer(xy)
+        prgb, dev_b, k2 = as_pointer(rgb)
+        psw, dev_c, k3 = as_pointer(sample_weight) if sample_weight is not None else (None, dev_a, None)
+        if not (dev_a == dev_b == dev_c):
+            raise ValueError("xy, rgb and sample_weight must all be host or all be device buffers")
+        if pinned_async:
+            if dev_a:
+                raise ValueError("pinned_async is for host arrays")
+            dev_a = 2  # PBRT_MEM_PINNED_ASYNC
+        _lib.check(_lib.lib.pbrt_film_add_samples_tile_rgb(
+            self._h, _lib.i32x4(sb.as4()), int(spp), pxy, prgb, psw, dev_a, int(mode)))
+
     def add_samples_tiles(self, sample_bounds, spp: int, xy, rgbw, sample_offsets=None, mode: int = SPLAT_EXACT) -> None:
         """Many tiles in one call: tile i has sample bounds `sample_bounds[i]` (x0, y0, x1, y1) and its pixel-major
         samples start at `sample_offsets[i]` (default: tiles packed back to back).  Same result as calling

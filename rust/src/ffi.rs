@@ -43,6 +43,16 @@ extern "C" {
         src_is_device: c_int,
         mode: c_int,
     ) -> c_int;
+    pub fn pbrt_film_add_samples_tile_rgb(
+        film: *mut PbrtFilm,
+        sample_bounds: *const i32,
+        spp: i32,
+        xy: *const c_float,
+        rgb: *const c_float,
+        sample_weight: *const c_float, // null = every weight is 1
+        src_is_device: c_int,
+        mode: c_int,
+    ) -> c_int;
     pub fn pbrt_film_resolve_rgb(film: *const PbrtFilm, splat_scale: c_float, out_rgb: *mut c_float, dst_is_device: c_int) -> c_int;
     pub fn pbrt_film_resolve_rgb8(film: *const PbrtFilm, splat_scale: c_float, out_rgb8: *mut u8, dst_is_device: c_int) -> c_int;
     pub fn pbrt_film_get_pixel_xyz(film: *const PbrtFilm, x: i32, y: i32, out: *mut c_float) -> c_int;

@@ -450,3 +450,63 @@ def test_pinned_async_pipeline_equals_synchronous_calls(gpu, orc):
     for i in range(3):
         assert np.array_equal(u32(outs[i].array), u32(want[i])), i
     assert np.array_equal(u32(a.read_pixels()), u32(b.read_pixels()))
+
+
+@pytest.mark.parametrize("weights", ["ones", "stream"])
+def test_separate_rgb_and_weight_streams_equal_interleaved(gpu, orc, weights):
+    """pbrt_film_add_samples_tile_rgb (AddSample's argument shape: L and sampleWeight apart; NULL weights = 1)
+    interleaves on the device and must give the film of the rgbw form bit for bit — from host memory, from
+    device memory and through the pinned double-buffered pipeline, odd sample counts included."""
+    res, spp = (67, 45), 3          # 67*45*3 samples: not a multiple of 4 -> the pack kernel's tail path
+    filt, kind, rad, p0, p1 = make_filter(gpu, "gaussian")
+    sb = (0, 0, *res)
+    xy, rgbw = oracle.synth_samples(orc, sb, spp, seed=9)
+    rng = np.random.default_rng(3)
+    if weights == "stream":
+        rgbw[:, 3] = rng.random(len(rgbw), dtype=np.float32) + 0.5
+    rgb = np.ascontiguousarray(rgbw[:, :3])
+    sw = np.ascontiguousarray(rgbw[:, 3]) if weights == "stream" else None
+    table = oracle.filter_table(orc, kind, rad, p0, p1)
+    of = OracleFilm(orc, res, [0, 0, 1, 1], rad, table)
+    ot = of.get_film_tile(sb)
+    orc.orc_ext_tile_add_samples(ot, len(xy), oracle.fp(xy), oracle.fp(rgbw))
+    of.merge(ot)
+    want = u32(of.pixels())
+
+    def fresh():
+        return gpu.Film.new(res, [[0, 0], [1, 1]], filt, 35.0, "x.pfm", 1.0, float("inf"))
+
+    f = fresh()                                    # host buffers
+    f.add_samples_tile_rgb(sb, spp, xy, rgb, sw, gpu.SPLAT_EXACT)
+    f.check()
+    assert np.array_equal(u32(f.read_pixels()), want)
+
+    f = fresh()                                    # device buffers
+    dxy, drgb = gpu.DeviceBuffer.from_numpy(xy), gpu.DeviceBuffer.from_numpy(rgb)
+    dsw = gpu.DeviceBuffer.from_numpy(sw) if sw is not None else None
+    f.add_samples_tile_rgb(sb, spp, dxy, drgb, dsw, gpu.SPLAT_EXACT)
+    f.check()
+    assert np.array_equal(u32(f.read_pixels()), want)
+
+    f = fresh()                                    # pinned, enqueued; twice, alternating staging sets
+    hxy, hrgb = gpu.PinnedBuffer(np.float32, xy.shape), gpu.PinnedBuffer(np.float32, rgb.shape)
+    hxy.array[:], hrgb.array[:] = xy, rgb
+    hsw = None
+    if sw is not None:
+        hsw = gpu.PinnedBuffer(np.float32, sw.shape)
+        hsw.array[:] = sw
+    g = fresh()
+    for film in (f, g, f):
+        film.add_samples_tile_rgb(sb, spp, hxy.array, hrgb.array, None if hsw is None else hsw.array,
+                                  gpu.SPLAT_EXACT, pinned_async=True)
+    gpu.synchronize()
+    g.check()
+    assert np.array_equal(u32(g.read_pixels()), want)
+    of.merge(_again(orc, of, sb, xy, rgbw))
+    assert np.array_equal(u32(f.read_pixels()), u32(of.pixels()))
+
+
+def _again(orc, of, sb, xy, rgbw):
+    ot = of.get_film_tile(sb)
+    orc.orc_ext_tile_add_samples(ot, len(xy), oracle.fp(xy), oracle.fp(rgbw))
+    return ot
