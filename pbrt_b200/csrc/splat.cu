@@ -528,7 +528,8 @@ static int env_int(const char *name, int dflt) {
 template <int H, int TW, bool FMA>
 static int launch_window(const SplatParams &P0) {
     SplatParams P = P0;
-    const size_t smem = WinSmem<H, TW, FMA>::bytes(P.spp);
+    // PBRT_B200_SMEM_PAD: experiment knob — extra dynamic shared memory per CTA, i.e. fewer resident CTAs
+    const size_t smem = WinSmem<H, TW, FMA>::bytes(P.spp) + (size_t)env_int("PBRT_B200_SMEM_PAD", 0);
     static bool attr_set = false;
     if (!attr_set) {
         PB_CUDA(cudaFuncSetAttribute(splat_window_kernel<H, TW, FMA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
