@@ -154,6 +154,8 @@ def test_argument_errors_need_no_device(pb):
     assert L.pbrt_film_check(None) == _lib.E_INVALID
     assert L.pbrt_film_get_sample_bounds(None, _lib.i32x4((0, 0, 0, 0))) == _lib.E_INVALID
     assert L.pbrt_film_add_samples_tile(None, _lib.i32x4((0, 0, 1, 1)), 1, None, None, 0, 0) == _lib.E_INVALID
+    assert L.pbrt_film_add_samples_tile_rgb(None, _lib.i32x4((0, 0, 1, 1)), 1, None, None, None, 0, 0) == _lib.E_INVALID
+    assert "null" in _lib.last_error()
     assert L.pbrt_film_destroy(None) == _lib.OK  # Drop of nothing
     h = C.c_void_p()
     assert L.pbrt_filter_create(99, 1.0, 1.0, 0.0, 0.0, C.byref(h)) == _lib.E_INVALID
