@@ -136,6 +136,17 @@ int pbrt_film_get_physical_extent(const PbrtFilm *film, float out[4]);  /* [T1] 
 int pbrt_film_tile_bounds(const PbrtFilm *film, const int32_t sample_bounds[4], int32_t out[4],
                           int64_t *pixel_count);
 /*
+ * [T1] Film::new's crop bounds (film.rs:92-101), get_sample_bounds (:166-175), get_physical_extent (:218-227) and
+ * get_film_tile's bounds (:264-273) as plain host functions: no film object, no device.  Any output pointer
+ * of pbrt_film_geometry may be NULL.  `owned` is the row block of shard `rank` of `nranks` (== cropped for 1).
+ * pbrt_film_geometry_tile_bounds clips against `clip` (the cropped bounds, or a shard's owned bounds).
+ */
+int pbrt_film_geometry(int32_t xres, int32_t yres, const float crop_window[4], const float filter_radius[2],
+                       float diagonal_mm, int rank, int nranks, int32_t cropped[4], int32_t owned[4],
+                       int32_t sample_bounds[4], float physical_extent[4]);
+int pbrt_film_geometry_tile_bounds(const int32_t clip[4], const float filter_radius[2], const int32_t sample_bounds[4],
+                                   int32_t out[4], int64_t *pixel_count);
+/*
  * [T1] Film::merge_film_tile (film.rs:313-326).  `rgbw` is the tile's Vec<FilmTilePixel>
  * (film.rs:39-42): 4 floats per pixel {contrib_sum.rgb, filter_weight_sum}, row-major over
  * `tile_bounds`.  The tile is consumed by value in the reference, so the buffer is only read.

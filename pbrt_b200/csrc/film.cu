@@ -312,11 +312,10 @@ extern "C" int pbrt_filter_table(const PbrtFilter *f, float table[256]) {
 
 // ===================================================================== film: host logic
 
-static int film_create_impl(int32_t xres, int32_t yres, const float crop[4], const float radius[2],
-                            const float table[256], float diagonal_mm, float scale, float max_lum, int rank,
-                            int nranks, PbrtFilm **out) {
-    if (int rc = pb::ensure_ready()) return rc;
-    if (!crop || !radius || !table || !out) return fail(PBRT_E_INVALID, "null argument");
+// Film::new's geometry (film.rs:92-101, :129, :450) into *f; no device involved
+static int film_geometry_init(PbrtFilm *f, int32_t xres, int32_t yres, const float crop[4], const float radius[2],
+                              float diagonal_mm, int rank, int nranks) {
+    if (!crop || !radius) return fail(PBRT_E_INVALID, "null argument");
     if (nranks < 1 || rank < 0 || rank >= nranks) return fail(PBRT_E_INVALID, "rank %d of %d", rank, nranks);
     // film.rs:92-101 — ceil(res * crop) per corner, then Bounds2i::from sorts each axis
     int64_t ax = pb::f2i(ceilf((float)xres * crop[0])), ay = pb::f2i(ceilf((float)yres * crop[1]));
@@ -324,14 +323,12 @@ static int film_create_impl(int32_t xres, int32_t yres, const float crop[4], con
     int64_t x0 = std::min(ax, bx), x1 = std::max(ax, bx), y0 = std::min(ay, by), y1 = std::max(ay, by);
     if (!pb::fits_i32(x0) || !pb::fits_i32(x1) || !pb::fits_i32(y0) || !pb::fits_i32(y1))
         return fail(PBRT_E_RANGE, "cropped pixel bounds do not fit the device's 32-bit coordinates");
-    PbrtFilm *f = new PbrtFilm();
     memset(f, 0, sizeof *f);
     f->xres = xres; f->yres = yres;
     memcpy(f->crop, crop, sizeof f->crop);
     f->radius[0] = radius[0]; f->radius[1] = radius[1];
     f->inv_radius[0] = 1.f / radius[0]; f->inv_radius[1] = 1.f / radius[1];  // film.rs:450
     f->diagonal_m = diagonal_mm * 0.001f;                                    // film.rs:129
-    f->scale = scale; f->max_lum = max_lum;
     f->cropped = Bounds{(int)x0, (int)y0, (int)x1, (int)y1};
     f->owned = f->cropped;
     if (nranks > 1) {
@@ -339,6 +336,18 @@ static int film_create_impl(int32_t xres, int32_t yres, const float crop[4], con
         f->owned.y0 = (int)(y0 + H * rank / nranks);
         f->owned.y1 = (int)(y0 + H * (rank + 1) / nranks);
     }
+    return PBRT_OK;
+}
+
+static int film_create_impl(int32_t xres, int32_t yres, const float crop[4], const float radius[2],
+                            const float table[256], float diagonal_mm, float scale, float max_lum, int rank,
+                            int nranks, PbrtFilm **out) {
+    if (int rc = pb::ensure_ready()) return rc;
+    if (!crop || !radius || !table || !out) return fail(PBRT_E_INVALID, "null argument");
+    PbrtFilm geo;
+    if (int rc = film_geometry_init(&geo, xres, yres, crop, radius, diagonal_mm, rank, nranks)) return rc;
+    PbrtFilm *f = new PbrtFilm(geo);
+    f->scale = scale; f->max_lum = max_lum;
     int64_t area = (int64_t)pb::bw(f->owned) * pb::bh(f->owned);
     f->npix = area > 0 ? area : 0;
     memcpy(f->table, table, sizeof f->table);
@@ -466,6 +475,31 @@ extern "C" int pbrt_film_tile_bounds(const PbrtFilm *f, const int32_t sb[4], int
         *pixel_count = area > 0 ? area : 0;             // film.rs:446
     }
     return PBRT_OK;
+}
+
+// [T1] the same computations without a film object or a device (tests; hosts that only need the bounds)
+extern "C" int pbrt_film_geometry(int32_t xres, int32_t yres, const float crop[4], const float radius[2],
+                                  float diagonal_mm, int rank, int nranks, int32_t cropped[4], int32_t owned[4],
+                                  int32_t sample_bounds[4], float physical_extent[4]) {
+    PbrtFilm geo;
+    if (int rc = film_geometry_init(&geo, xres, yres, crop, radius, diagonal_mm, rank, nranks)) return rc;
+    if (cropped) put_bounds(geo.cropped, cropped);
+    if (owned) put_bounds(geo.owned, owned);
+    if (sample_bounds)
+        if (int rc = pbrt_film_get_sample_bounds(&geo, sample_bounds)) return rc;
+    if (physical_extent)
+        if (int rc = pbrt_film_get_physical_extent(&geo, physical_extent)) return rc;
+    return PBRT_OK;
+}
+
+extern "C" int pbrt_film_geometry_tile_bounds(const int32_t clip[4], const float radius[2], const int32_t sb[4],
+                                              int32_t out[4], int64_t *pixel_count) {
+    if (!clip || !radius || !sb || !out) return fail(PBRT_E_INVALID, "null argument");
+    PbrtFilm geo;
+    memset(&geo, 0, sizeof geo);
+    geo.radius[0] = radius[0]; geo.radius[1] = radius[1];
+    geo.owned = Bounds{clip[0], clip[1], clip[2], clip[3]};
+    return pbrt_film_tile_bounds(&geo, sb, out, pixel_count);
 }
 
 // ===================================================================== kernels: merge

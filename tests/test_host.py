@@ -130,3 +130,88 @@ def test_to_byte_slices_hold_at_most_one_threshold():
     for start in range(first, one, 1 << shift):
         inside = [t for t in thr if start < t < start + (1 << shift)]
         assert len(inside) <= 1, (hex(start), inside)
+
+
+def _geometry(pb, res, crop, radius, diag=35.0, rank=0, nranks=1):
+    import ctypes as C
+
+    from pbrt_b200 import _lib
+
+    cropped, owned, sb = (C.c_int32 * 4)(), (C.c_int32 * 4)(), (C.c_int32 * 4)()
+    ext = (C.c_float * 4)()
+    _lib.check(_lib.lib.pbrt_film_geometry(res[0], res[1], _lib.f32arr(crop), _lib.f32arr(radius), diag, rank, nranks,
+                                           cropped, owned, sb, ext))
+    return tuple(cropped), tuple(owned), tuple(sb), tuple(ext)
+
+
+def test_film_geometry_reference_doctests_without_a_device(pb, kats):
+    """film.rs:161-164, :197-216, :252-262 through the library's host logic (no GPU needed)."""
+    import ctypes as C
+
+    from pbrt_b200 import _lib
+
+    k = kats["film_1920x1080_crop_quarter_box8"]
+    cropped, owned, sb, _ = _geometry(pb, k["resolution"], k["crop"], [8.0, 8.0])
+    assert sb == (472, 262, 1448, 818)
+    assert cropped == owned == (480, 270, 1440, 810)
+    out, n = (C.c_int32 * 4)(), C.c_int64()
+    for sample_bounds, want in (((0, 0, 1920, 1080), (480, 270, 1440, 810)), ((500, 500, 600, 600), (492, 492, 608, 608))):
+        _lib.check(_lib.lib.pbrt_film_geometry_tile_bounds(_lib.i32x4(cropped), _lib.f32arr([8.0, 8.0]),
+                                                           _lib.i32x4(sample_bounds), out, C.byref(n)))
+        assert tuple(out) == want and n.value == (want[2] - want[0]) * (want[3] - want[1])
+    for c in kats["film_800x600_physical_extent"]["crops"]:
+        ext = _geometry(pb, [800, 600], c, [8.0, 8.0], diag=100.0)[3]
+        assert ext == tuple(np.float32(v) for v in (-0.04, -0.03, 0.04, 0.03))
+
+
+def test_film_geometry_matches_oracle_on_random_films(pb, orc):
+    """Crop, sample, tile bounds (ints, bit-exact) and physical extent (f32, exact) against the oracle for random
+    resolutions, crop windows (including inverted and empty ones), radii and sample bounds (including ones that
+    miss the film)."""
+    import ctypes as C
+
+    import oracle
+    from pbrt_b200 import _lib
+
+    rng = np.random.default_rng(2024)
+    table = np.ones(256, dtype=np.float32)
+    out, n = (C.c_int32 * 4)(), C.c_int64()
+    for _ in range(300):
+        res = [int(rng.integers(1, 9000)), int(rng.integers(1, 5000))]
+        crop = [float(np.float32(v)) for v in rng.random(4)]
+        if rng.random() < 0.5:
+            crop = [min(crop[0], crop[2]), min(crop[1], crop[3]), max(crop[0], crop[2]), max(crop[1], crop[3])]
+        if rng.random() < 0.2:
+            crop = [0.0, 0.0, 1.0, 1.0]
+        radius = [float(np.float32(rng.choice([0.5, 1.0, 1.5, 2.0, 3.0, 4.0, 8.0, rng.random() * 6 + 0.1]))) for _ in range(2)]
+        diag = float(np.float32(rng.random() * 100 + 1))
+        of = oracle.OracleFilm(orc, res, crop, radius, table, diagonal_mm=diag)
+        cropped, owned, sb, ext = _geometry(pb, res, crop, radius, diag)
+        assert cropped == tuple(of.cropped()) and owned == cropped
+        assert sb == tuple(of.sample_bounds())
+        assert np.array_equal(np.asarray(ext, np.float32).view(np.uint32),
+                              np.asarray(of.physical_extent(), np.float32).view(np.uint32))
+        for _ in range(4):
+            x0, y0 = int(rng.integers(-50, res[0] + 50)), int(rng.integers(-50, res[1] + 50))
+            q = (x0, y0, x0 + int(rng.integers(0, 200)), y0 + int(rng.integers(0, 200)))
+            _lib.check(_lib.lib.pbrt_film_geometry_tile_bounds(_lib.i32x4(cropped), _lib.f32arr(radius), _lib.i32x4(q),
+                                                               out, C.byref(n)))
+            want = tuple(of.tile_bounds(q))
+            assert tuple(out) == want, (res, crop, radius, q)
+            # FilmTile::new allocates max(0, area) pixels and Bounds2i::area is a plain product (film.rs:446,
+            # bounds.rs:195-198): a tile inverted on both axes has a positive count, in the reference too
+            t = of.get_film_tile(q)
+            assert n.value == orc.orc_tile_pixel_count(t), (res, crop, radius, q, want)
+            orc.orc_tile_free(t)
+
+
+def test_sharded_geometry_partitions_the_rows(pb):
+    """pbrt_film_create_sharded's row blocks: disjoint, in order, covering the cropped bounds."""
+    for res, crop, world in (([1920, 1080], [0, 0, 1, 1], 8), ([640, 483], [0.1, 0.2, 0.9, 0.77], 3), ([7680, 4320], [0, 0, 1, 1], 8)):
+        rows = []
+        for r in range(world):
+            cropped, owned, _, _ = _geometry(pb, res, crop, [2.0, 2.0], rank=r, nranks=world)
+            assert owned[0] == cropped[0] and owned[2] == cropped[2]
+            rows.append((owned[1], owned[3]))
+        assert rows[0][0] == cropped[1] and rows[-1][1] == cropped[3]
+        assert all(a[1] == b[0] for a, b in zip(rows, rows[1:]))
