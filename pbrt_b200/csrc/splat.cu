@@ -18,7 +18,7 @@
 //     pixel pitch so that lanes reading sample s of consecutive pixels hit distinct banks.
 //     The gather then costs, per (sample, column): one LDS.128 + one LDS.32/64, the ifx index
 //     (5 FP ops), and per window row one IDP.4A (table address) + LDS(table) + 3 FMUL + 2 FADD2
-//     (exact) or 2 FFMA2 (PBRT_SPLAT_FMA).  ptxas fuses a packed mul feeding a packed add into one
+//     (exact) or 3 FFMA + FADD (PBRT_SPLAT_FMA).  ptxas fuses a packed mul feeding a packed add into one
 //     FFMA2 even under --fmad=false, so the exact variant multiplies in scalar registers and only
 //     adds packed (tests/test_abi.py checks the SASS).
 //     When the oldest window row can no longer be reached it is converted (rgb_to_xyz) and
@@ -159,12 +159,6 @@ __device__ __forceinline__ u64 add2(u64 a, u64 b) {
     asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
     return r;
 }
-__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
-    u64 r;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
-    return r;
-}
-
 // Row bytes of a sample: for each of the ROWS = 2h+1 output rows of the window, the filter-table
 // row (ify, 0..15) it reads — or 16, the all-zero table row, when the sample's footprint does not
 // reach that row (only the two outermost rows can be unreachable).  One byte per row, 1..3 words,
@@ -189,12 +183,11 @@ constexpr int TAB_ZERO = 16;
 // (row, column) table indices differ by at most 2 each.  With a pitch of 21 entries, 21*drow + dcol is
 // never 0 modulo the 32 four-byte (or 16 eight-byte) bank slots in that range, so the lookups of a warp
 // fall on distinct banks (a pitch of 17 made (row, col) collide with (row+1, col-1): 30 % extra wavefronts).
-// Entries are (w, w) pairs (8 B) for the FMA variant, whose FFMA2 wants the packed operand, and single
-// weights (4 B) for the exact variant: half the shared-memory wavefronts per lookup.  The h = 4 FMA
-// variant keeps pitch 17: its larger records leave no room for the bigger table without losing a CTA per SM.
+// Entries are single 4-byte weights in both variants (measured: scalar multiplies / FFMAs beat the packed
+// forms here, tools/ubench_gather.cu).
 template <int H, bool FMA> struct TabCfg {
-    static constexpr int ENTRY = FMA ? 8 : 4;
-    static constexpr int ROW_BYTES = ((H == 4 && FMA) ? 17 : 21) * ENTRY;
+    static constexpr int ENTRY = 4;
+    static constexpr int ROW_BYTES = 21 * ENTRY;
     static constexpr int BYTES = (17 * ROW_BYTES + 127) / 128 * 128;
 };
 
@@ -228,12 +221,6 @@ __device__ __forceinline__ unsigned bin_bits(float v) {
 // Table fetch.  Deliberately not `volatile`: the table is constant once the kernel's first barrier has
 // passed and the address depends on data read after it, so the compiler may schedule these loads
 // early across the unrolled samples without being able to hoist them too far.
-__device__ __forceinline__ u64 lds_pair(unsigned addr) {
-    u64 v;
-    asm("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(addr));
-    return v;
-}
-
 __device__ __forceinline__ float lds_f32(unsigned addr) {
     float v;
     asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
@@ -269,8 +256,7 @@ __global__ void __launch_bounds__(TW) splat_window_kernel(SplatParams P) {
     for (int i = tid; i < 17 * 17; i += TW) {
         const int ty = i / 17, tx = i - ty * 17;
         const float w = (ty < 16 && tx < 16) ? P.table[ty * 16 + tx] : 0.f;
-        if (FMA) *reinterpret_cast<float2 *>(smem + ty * TAB_ROW_BYTES + tx * 8) = make_float2(w, w);
-        else *reinterpret_cast<float *>(smem + ty * TAB_ROW_BYTES + tx * 4) = w;
+        *reinterpret_cast<float *>(smem + ty * TAB_ROW_BYTES + tx * 4) = w;
     }
     // shared-window address of the table, kept opaque so it lives in a register instead of being
     // rematerialised (S2UR/ULEA) at every use
@@ -384,20 +370,22 @@ __global__ void __launch_bounds__(TW) splat_window_kernel(SplatParams P) {
                     // all window rows of one sample against this column; ifx = table column (TAB_ZERO adds exact zeros)
                     auto taps = [&](const float4 a, const RB yb, const unsigned ifx) {
                         const unsigned xcol = tab_base + ifx * TAB_ENTRY;  // shared address of table column ifx
-                        const u64 Lrg = pack2(a.x, a.y);
-                        const u64 Lb1 = pack2(a.z, 1.f);
 #pragma unroll
                         for (int j = 0; j < ROWS; ++j) {
                             // row byte j times the table's row pitch, plus the column address, in one dot-product
                             // instruction: dp4a(bytes, pitch in byte lane j, xcol)
                             const unsigned waddr = __dp4a(rb_word(yb, j >> 2), (unsigned)TAB_ROW_BYTES << (8 * (j & 3)), xcol);
+                            const float w = lds_f32(waddr);
                             if (FMA) {
-                                const u64 ww = lds_pair(waddr);
-                                acc_rg[j] = fma2(Lrg, ww, acc_rg[j]);
-                                acc_bw[j] = fma2(Lb1, ww, acc_bw[j]);
+                                // three scalar FFMAs and one FADD on the halves of the accumulator pairs: cheaper to
+                                // dispatch than two packed FFMA2 (profiles/r1_ubench_gather.txt)
+                                float r, g, b, ws;
+                                unpack2(acc_rg[j], r, g);
+                                unpack2(acc_bw[j], b, ws);
+                                acc_rg[j] = pack2(__fmaf_rn(a.x, w, r), __fmaf_rn(a.y, w, g));
+                                acc_bw[j] = pack2(__fmaf_rn(a.z, w, b), ws + w);
                             } else {
                                 // products by scalar multiplies (rounded like the CPU's), sums packed: (r*w, g*w) and (b*w, w)
-                                const float w = lds_f32(waddr);
                                 acc_rg[j] = add2(acc_rg[j], pack2(a.x * w, a.y * w));
                                 acc_bw[j] = add2(acc_bw[j], pack2(a.z * w, w));
                             }

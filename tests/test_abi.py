@@ -63,8 +63,8 @@ def test_exact_splat_kernel_has_no_fused_accumulate(pb):
             for ins in ffma2:
                 assert re.search(r", U?R\d+\.F32 ;$", ins), f"{name}: fused accumulate {ins}"
             checked += 1
-        else:  # fma mode accumulates with the fused form
-            assert any(re.search(r"\.F32x2\.HI_LO ;$", ins) for ins in ffma2), name
+        else:  # fma mode accumulates with (scalar) fused multiply-adds: many more FFMA than the exact twin's divisions
+            assert len(re.findall(r"FFMA R", b)) > 100 and not fadd2, name
     assert checked >= 4
 
 
