@@ -33,6 +33,26 @@ extern "C" {
     pub fn pbrt_film_get_sample_bounds(film: *const PbrtFilm, out: *mut i32) -> c_int;
     pub fn pbrt_film_get_physical_extent(film: *const PbrtFilm, out: *mut c_float) -> c_int;
     pub fn pbrt_film_tile_bounds(film: *const PbrtFilm, sample_bounds: *const i32, out: *mut i32, pixel_count: *mut i64) -> c_int;
+    pub fn pbrt_film_geometry(
+        xres: i32,
+        yres: i32,
+        crop_window: *const c_float,
+        filter_radius: *const c_float,
+        diagonal_mm: c_float,
+        rank: c_int,
+        nranks: c_int,
+        cropped: *mut i32,
+        owned: *mut i32,
+        sample_bounds: *mut i32,
+        physical_extent: *mut c_float,
+    ) -> c_int;
+    pub fn pbrt_film_geometry_tile_bounds(
+        clip: *const i32,
+        filter_radius: *const c_float,
+        sample_bounds: *const i32,
+        out: *mut i32,
+        pixel_count: *mut i64,
+    ) -> c_int;
     pub fn pbrt_film_merge_tile(film: *mut PbrtFilm, tile_bounds: *const i32, rgbw: *const c_float, src_is_device: c_int) -> c_int;
     pub fn pbrt_film_add_samples_tile(
         film: *mut PbrtFilm,
