@@ -109,7 +109,7 @@ struct PbrtFilm {
     size_t d_idx_bytes;
     pb::Bounds idx_box;
     int idx_cells_x;
-    size_t idx_off[4];
+    size_t idx_off[5];
     int64_t idx_need;        // pixels the batch's rgbw buffer must hold
     void *d_tile_desc;       // add_samples_tiles: SplatTile array (grow-only)
     size_t tile_desc_bytes;

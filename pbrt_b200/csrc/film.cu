@@ -531,7 +531,19 @@ struct MergeIndex {
     const int *cell_tiles;
     const int4 *tile_bounds;
     const long long *tile_offset;
+    const struct CellHead *cell_head;
 };
+
+// The first four tiles of a cell, inline: one 128-byte fetch tells a CTA everything it needs for the usual
+// case (a cell of a regular tiling is covered by at most 2x2 tiles), instead of the three dependent global
+// loads of the CSR walk (cell_start -> cell_tiles -> tile_bounds/offset) ahead of the first pixel load.
+struct __align__(16) CellHead {
+    int count, pad0, pad1, pad2;
+    int4 bounds[4];
+    long long offset[4];
+    long long pad3[2];
+};
+static_assert(sizeof(CellHead) == 128, "one cache line per cell");
 
 // One CTA per 16x16 cell: the cell's tile list (bounds, offsets) is the same for all 256 pixels, so it
 // is fetched into shared memory once and read back as broadcasts; the per-pixel work is then one
@@ -540,37 +552,48 @@ constexpr int MERGE_CHUNK = 32;
 
 __global__ void __launch_bounds__(256) merge_tiles_kernel(float4 *__restrict__ film, Bounds owned, MergeIndex ix,
                                                           const float4 *__restrict__ tiles) {
+    __shared__ CellHead s_head;
     __shared__ int4 s_bounds[MERGE_CHUNK];
     __shared__ long long s_offset[MERGE_CHUNK];
     const int cell = blockIdx.y * ix.cells_x + blockIdx.x;
-    const int beg = ix.cell_start[cell], end = ix.cell_start[cell + 1];
-    if (beg == end) return;
+    if (threadIdx.x < 8)
+        reinterpret_cast<int4 *>(&s_head)[threadIdx.x] = reinterpret_cast<const int4 *>(ix.cell_head + cell)[threadIdx.x];
     const int x = ix.box.x0 + blockIdx.x * 16 + (threadIdx.x & 15);
     const int y = ix.box.y0 + blockIdx.y * 16 + (threadIdx.x >> 4);
     const bool in_box = x < ix.box.x1 && y < ix.box.y1;
     const size_t fo = (size_t)(y - owned.y0) * (owned.x1 - owned.x0) + (x - owned.x0);
     float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (in_box) p = film[fo];
+    if (in_box) p = film[fo];  // in flight while the head arrives
+    __syncthreads();
+    const int total = s_head.count;
+    if (total == 0) return;
     bool touched = false;
-    for (int k0 = beg; k0 < end; k0 += MERGE_CHUNK) {
-        const int n = min(MERGE_CHUNK, end - k0);
-        __syncthreads();
-        if ((int)threadIdx.x < n) {
-            const int t = ix.cell_tiles[k0 + threadIdx.x];
-            s_bounds[threadIdx.x] = ix.tile_bounds[t];
-            s_offset[threadIdx.x] = ix.tile_offset[t];
-        }
-        __syncthreads();
-        if (in_box) {
-            for (int k = 0; k < n; ++k) {  // ascending tile index: the order sequential merge_film_tile calls would use
-                const int4 b = s_bounds[k];
-                if (x < b.x || x >= b.z || y < b.y || y >= b.w) continue;
-                const float4 v = pb::ldg_stream(&tiles[s_offset[k] + (size_t)(y - b.y) * (b.z - b.x) + (x - b.x)]);
-                float X, Y, Z;
-                pb::rgb_to_xyz(v.x, v.y, v.z, X, Y, Z);
-                p.x += X; p.y += Y; p.z += Z; p.w += v.w;
-                touched = true;
+    auto add_tile = [&](const int4 b, long long off) {  // ascending tile index: the order sequential merge_film_tile calls would use
+        if (x < b.x || x >= b.z || y < b.y || y >= b.w) return;
+        const float4 v = pb::ldg_stream(&tiles[off + (size_t)(y - b.y) * (b.z - b.x) + (x - b.x)]);
+        float X, Y, Z;
+        pb::rgb_to_xyz(v.x, v.y, v.z, X, Y, Z);
+        p.x += X; p.y += Y; p.z += Z; p.w += v.w;
+        touched = true;
+    };
+    if (in_box) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (k < total) add_tile(s_head.bounds[k], s_head.offset[k]);
+    }
+    if (total > 4) {  // the rest of a crowded cell through the CSR, a chunk at a time
+        const int beg = ix.cell_start[cell] + 4, end = ix.cell_start[cell + 1];
+        for (int k0 = beg; k0 < end; k0 += MERGE_CHUNK) {
+            const int n = min(MERGE_CHUNK, end - k0);
+            __syncthreads();
+            if ((int)threadIdx.x < n) {
+                const int t = ix.cell_tiles[k0 + threadIdx.x];
+                s_bounds[threadIdx.x] = ix.tile_bounds[t];
+                s_offset[threadIdx.x] = ix.tile_offset[t];
             }
+            __syncthreads();
+            if (in_box)
+                for (int k = 0; k < n; ++k) add_tile(s_bounds[k], s_offset[k]);
         }
     }
     if (touched) film[fo] = p;
@@ -649,11 +672,25 @@ extern "C" int pbrt_film_merge_tiles(PbrtFilm *f, int32_t ntiles, const int32_t 
             for (int gy = (tb[i].y - box.y0) >> 4; gy <= (tb[i].w - 1 - box.y0) >> 4; ++gy)
                 for (int gx = (tb[i].x - box.x0) >> 4; gx <= (tb[i].z - 1 - box.x0) >> 4; ++gx) list[(size_t)fill[(size_t)gy * cx + gx]++] = i;
         }
-        // one upload: [start | list | bounds | offsets], each part 16-byte aligned
+        // the first four tiles of every cell, inline
+        std::vector<CellHead> heads((size_t)cx * cy);
+        memset(heads.data(), 0, heads.size() * sizeof(CellHead));
+        for (size_t c = 0; c < heads.size(); ++c) {
+            heads[c].count = start[c + 1] - start[c];
+            for (int k = 0; k < std::min(heads[c].count, 4); ++k) {
+                const int t = list[(size_t)start[c] + k];
+                heads[c].bounds[k] = tb[t];
+                heads[c].offset[k] = off[t];
+            }
+        }
+        // one upload: [start | list | bounds | offsets | heads], each part 16-byte aligned
         auto align16 = [](size_t v) { return (v + 15) & ~size_t(15); };
         const size_t b0 = 0, b1 = align16(start.size() * sizeof(int)), b2 = b1 + align16(list.size() * sizeof(int));
-        const size_t b3 = b2 + tb.size() * sizeof(int4), b4 = b3 + off.size() * sizeof(long long);
-        std::vector<unsigned char> blob(b4);
+        const size_t b3 = b2 + tb.size() * sizeof(int4);
+        const size_t b4 = (b3 + off.size() * sizeof(long long) + 127) & ~size_t(127);
+        const size_t b5 = b4 + heads.size() * sizeof(CellHead);
+        std::vector<unsigned char> blob(b5);
+        memcpy(&blob[b4], heads.data(), heads.size() * sizeof(CellHead));
         memcpy(&blob[b0], start.data(), start.size() * sizeof(int));
         if (!list.empty()) memcpy(&blob[b1], list.data(), list.size() * sizeof(int));
         memcpy(&blob[b2], tb.data(), tb.size() * sizeof(int4));
@@ -677,7 +714,7 @@ extern "C" int pbrt_film_merge_tiles(PbrtFilm *f, int32_t ntiles, const int32_t 
         memcpy(f->idx_offsets, offsets, (size_t)ntiles * sizeof(int64_t));
         f->idx_box = box;
         f->idx_cells_x = cx;
-        f->idx_off[0] = b0; f->idx_off[1] = b1; f->idx_off[2] = b2; f->idx_off[3] = b3;
+        f->idx_off[0] = b0; f->idx_off[1] = b1; f->idx_off[2] = b2; f->idx_off[3] = b3; f->idx_off[4] = b4;
         f->idx_need = need;
         f->idx_ntiles = ntiles;
     }
@@ -699,6 +736,7 @@ extern "C" int pbrt_film_merge_tiles(PbrtFilm *f, int32_t ntiles, const int32_t 
     ix.cell_tiles = (const int *)((char *)d_blob + b1);
     ix.tile_bounds = (const int4 *)((char *)d_blob + b2);
     ix.tile_offset = (const long long *)((char *)d_blob + b3);
+    ix.cell_head = (const CellHead *)((char *)d_blob + f->idx_off[4]);
     dim3 grid(cx, (pb::bh(box) + 15) / 16);  // one CTA per 16x16 cell of the index
     merge_tiles_kernel<<<grid, 256, 0, ctx().stream>>>(f->d_xyzw, f->owned, ix, d_tiles);
     PB_LAUNCH_CHECK("merge_tiles_kernel");

@@ -158,6 +158,29 @@ def test_batched_merge_equals_sequential_oracle(gpu, orc, crop):
     assert np.array_equal(u32(film.read_pixels()), u32(of.pixels()))
 
 
+def test_batched_merge_of_crowded_cells(gpu, orc):
+    """Many large random tiles over a small film: every 16x16 cell is covered by far more than the four tiles its
+    inline head holds (and by more than one 32-tile chunk of the overflow list), so the CSR walk is exercised;
+    pixels must still receive the tiles in ascending order, bit for bit."""
+    res, r = (72, 56), 1.5
+    filt = gpu.GaussianFilter((r, r), 2.0)
+    table = oracle.filter_table(orc, 2, (r, r), 2.0)
+    film = gpu.Film.new(res, [[0, 0], [1, 1]], filt, 35.0, "x.pfm", 1.0, 1.0)
+    of = OracleFilm(orc, res, [0, 0, 1, 1], (r, r), table)
+    rng = np.random.default_rng(11)
+    sbs = []
+    for _ in range(160):
+        x0, y0 = int(rng.integers(0, 50)), int(rng.integers(0, 36))
+        sbs.append((x0, y0, x0 + int(rng.integers(6, 40)), y0 + int(rng.integers(6, 30))))
+    sbs += [(10, 10, 10, 30), (0, 0, 72, 56)]  # an empty tile and one covering everything
+    for _ in range(2):
+        tiles = _random_tiles(film, of, orc, rng, sbs)
+        film.merge_film_tiles([t for t, _ in tiles])
+        for _, ot in tiles:
+            of.merge(ot)
+    assert np.array_equal(u32(film.read_pixels()), u32(of.pixels()))
+
+
 def test_resolve_vs_oracle_with_splats_scale_and_zero_weight(gpu, orc):
     res = (97, 61)  # not a multiple of the resolve block: exercises the ragged tail
     film = gpu.Film.new(res, [[0, 0], [1, 1]], gpu.BoxFilter.new([0.5, 0.5]), 35.0, "x.pfm", 0.75, float("inf"))
