@@ -18,7 +18,7 @@ constexpr int TW = 128, H = 2, ROWS = 5, SPP = 16, PITCH = 17, NPX = TW + 2 * H;
 constexpr int TAB_ROW_BYTES = 21 * 4, TAB_BYTES = 1536;
 
 template <int UNROLL, int MODE>
-__global__ void __launch_bounds__(TW) gather_only(float *out, int reps, float irx16, int never) {
+__global__ void __launch_bounds__(TW) gather_only(float *out, int reps, float irx16, int never, const unsigned *flagp) {
     extern __shared__ __align__(16) unsigned char smem[];
     float4 *s_a = reinterpret_cast<float4 *>(smem + TAB_BYTES);
     uint2 *s_b = reinterpret_cast<uint2 *>(smem + TAB_BYTES + NPX * PITCH * 16);
@@ -34,6 +34,7 @@ __global__ void __launch_bounds__(TW) gather_only(float *out, int reps, float ir
     unsigned tab_base = (unsigned)__cvta_generic_to_shared(smem);
     asm volatile("mov.u32 %0, %0;" : "+r"(tab_base));
     const float fx = (float)(tid + H);
+    const unsigned flags = flagp[0];
     u64 acc_rg[ROWS], acc_bw[ROWS];
     float sr[ROWS], sg[ROWS], sb[ROWS], sw[ROWS];
 #pragma unroll
@@ -43,17 +44,38 @@ __global__ void __launch_bounds__(TW) gather_only(float *out, int reps, float ir
         for (int d = -H + 1; d <= H - 1; ++d) {
             const float4 *pa = s_a + (tid + H + d) * PITCH;
             const uint2 *pb = s_b + (tid + H + d) * PITCH;
+            for (int s0 = 0; s0 < SPP; s0 += 8) {
+            const bool upper = MODE == 4 ? ((flags >> (s0 >> 3)) & 1) != 0 : false;   // warp-uniform, from memory
+            if (upper) {
 #pragma unroll UNROLL
-            for (int s = 0; s < SPP; ++s) {
+            for (int s = s0; s < s0 + 8; ++s) {
+                const bool upper = true;
                 const float4 a = pa[s];
                 const uint2 yb = pb[s];
                 const unsigned ifx = bin_bits((fx - a.w) * irx16) & 0xFu;
                 const unsigned xcol = tab_base + ifx * 4;
 #pragma unroll
                 for (int j = 0; j < ROWS; ++j) {
+                    if (MODE == 4 && j == (upper ? ROWS - 1 : 0)) continue;
                     const unsigned waddr = __dp4a(j < 4 ? yb.x : yb.y, (unsigned)TAB_ROW_BYTES << (8 * (j & 3)), xcol);
                     const float w = lds_f32(waddr);
-                    if (MODE == 0) {          // exact, packed adds (the kernel today)
+                    acc_rg[j] = add2(acc_rg[j], pack2(a.x * w, a.y * w));
+                    acc_bw[j] = add2(acc_bw[j], pack2(a.z * w, w));
+                }
+            }
+            } else {
+#pragma unroll UNROLL
+            for (int s = s0; s < s0 + 8; ++s) {
+                const float4 a = pa[s];
+                const uint2 yb = pb[s];
+                const unsigned ifx = bin_bits((fx - a.w) * irx16) & 0xFu;
+                const unsigned xcol = tab_base + ifx * 4;
+#pragma unroll
+                for (int j = 0; j < ROWS; ++j) {
+                    if (MODE == 4 && j == (upper ? ROWS - 1 : 0)) continue;   // the row this sample type never reaches
+                    const unsigned waddr = __dp4a(j < 4 ? yb.x : yb.y, (unsigned)TAB_ROW_BYTES << (8 * (j & 3)), xcol);
+                    const float w = lds_f32(waddr);
+                    if (MODE == 0 || MODE == 4) {          // exact, packed adds (the kernel today)
                         acc_rg[j] = add2(acc_rg[j], pack2(a.x * w, a.y * w));
                         acc_bw[j] = add2(acc_bw[j], pack2(a.z * w, w));
                     } else if (MODE == 1) {   // exact, scalar adds
@@ -66,6 +88,8 @@ __global__ void __launch_bounds__(TW) gather_only(float *out, int reps, float ir
                         asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc_bw[j]) : "l"(pack2(a.z, 1.f)), "l"(ww));
                     }
                 }
+            }
+            }
             }
         }
     }
@@ -86,11 +110,12 @@ static void run(int ctas_per_sm) {
     int per_sm = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gather_only<UNROLL, MODE>, TW, smem);
     float *d; cudaMalloc(&d, 4);
+    unsigned *dflags; cudaMalloc(&dflags, 4); unsigned hf = 1u; cudaMemcpy(dflags, &hf, 4, cudaMemcpyHostToDevice);
     const int reps = 400;
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-    gather_only<UNROLL, MODE><<<148 * per_sm, TW, smem>>>(d, reps, 8.f, 7);
+    gather_only<UNROLL, MODE><<<148 * per_sm, TW, smem>>>(d, reps, 8.f, 7, dflags);
     cudaEventRecord(e0);
-    gather_only<UNROLL, MODE><<<148 * per_sm, TW, smem>>>(d, reps, 8.f, 7);
+    gather_only<UNROLL, MODE><<<148 * per_sm, TW, smem>>>(d, reps, 8.f, 7, dflags);
     cudaEventRecord(e1); cudaEventSynchronize(e1);
     float ms; cudaEventElapsedTime(&ms, e0, e1);
     int clk; cudaDeviceGetAttribute(&clk, cudaDevAttrClockRate, 0);
@@ -109,5 +134,7 @@ int main() {
     for (int c : {2, 4}) run<8, 1>(c);
     for (int c : {2, 4}) run<8, 2>(c);
     for (int c : {2, 4}) run<8, 3>(c);
+    for (int c : {2, 4}) run<8, 4>(c);
+    for (int c : {4}) run<4, 4>(c);
     return 0;
 }
