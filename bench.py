@@ -249,6 +249,9 @@ def main():
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a B200: libpbrt_b200 has no CPU fallback")
+    # host side of the end-to-end path: keep this rank's threads (and, by first touch, its pinned sample buffers)
+    # on the cores next to its GPU; a no-op on single-node hosts or when NVML cannot tell
+    bound_cores = pb.bind_host_to_device_numa(local_rank) if world > 1 else None
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -427,7 +430,7 @@ def main():
                        "film": [W, H], "spp_per_pass": spp, "filter": wl["filter"], "radius": list(wl["radius"]),
                        "mode": args.mode, "samples_per_step": n_unique_total, "samples_per_rank_incl_halo": n_local,
                        "cache": "inputs_exceed_l2" if n_local * 24 > 126e6 else "inputs_fit_l2",
-                       "parallelism": f"rows x{world}", "tier": "extension (no reference parity): splat; merge+resolve are Tier 1"},
+                       "parallelism": f"rows x{world}", "host_cores_bound": (len(bound_cores) if bound_cores else None), "tier": "extension (no reference parity): splat; merge+resolve are Tier 1"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": clocks,
             "assemble": {"resolve_then_nccl_allgather_ms": assemble_ms, "fused_resolve_peer_store_ms": assemble_fused_ms,

@@ -13,6 +13,40 @@ def init(device: int = 0) -> None:
     _lib.check(_lib.lib.pbrt_b200_init(int(device)))
 
 
+def bind_host_to_device_numa(device: int = 0) -> list[int] | None:
+    """Pin the calling process to the CPU cores next to `device` (NVML's ideal CPU affinity for the GPU).
+
+    Host buffers allocated afterwards (first touch) then sit in the NUMA node whose PCIe root the GPU hangs
+    off, which is what the host-fed path needs when several ranks stream samples at once: without it every
+    rank's uploads cross the socket interconnect.  Returns the core list, or None when NVML cannot tell
+    (then nothing is changed).  Host-side plumbing only; no effect on results.
+    """
+    import os
+
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+        index = int(device)
+        if visible:
+            ids = [v.strip() for v in visible.split(",") if v.strip()]
+            if index < len(ids) and ids[index].isdigit():
+                index = int(ids[index])
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cores = [64 * w + b for w, mask in enumerate(words) for b in range(64) if (int(mask) >> b) & 1]
+        allowed = os.sched_getaffinity(0)
+        cores = [c for c in cores if c in allowed]
+        if not cores:
+            return None
+        os.sched_setaffinity(0, cores)
+        return cores
+    except Exception:  # noqa: BLE001 - best effort: NVML absent, cgroup restrictions, ...
+        return None
+
+
 def set_stream(cuda_stream_ptr: int | None) -> None:
     """Run subsequent work on a caller-owned cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream).
 
