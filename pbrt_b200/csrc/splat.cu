@@ -368,8 +368,10 @@ __global__ void __launch_bounds__(TW) splat_window_kernel(SplatParams P) {
                     const float4 *pa = s_a + pl * pitch;
                     const RB *pb = s_b + pl * pitch;
                     // all window rows of one sample against this column; ifx = table column (TAB_ZERO adds exact zeros)
-                    auto taps = [&](const float4 a, const RB yb, const unsigned ifx) {
-                        const unsigned xcol = tab_base + ifx * TAB_ENTRY;  // shared address of table column ifx
+                    // `ifx_bits`: a word whose low byte is the table column and whose other bytes do not matter
+                    auto taps = [&](const float4 a, const RB yb, const unsigned ifx_bits) {
+                        // shared address of the table column: low byte x 4 + base, in one dot-product instruction
+                        const unsigned xcol = __dp4a(ifx_bits, (unsigned)TAB_ENTRY, tab_base);
 #pragma unroll
                         for (int j = 0; j < ROWS; ++j) {
                             // row byte j times the table's row pitch, plus the column address, in one dot-product
@@ -395,7 +397,7 @@ __global__ void __launch_bounds__(TW) splat_window_kernel(SplatParams P) {
 #pragma unroll kWinUnroll
                         for (int s = 0; s < spp; ++s) {
                             const float4 a = pa[s];
-                            taps(a, pb[s], bin_bits((fx - a.w) * irx16) & 0xFu);
+                            taps(a, pb[s], bin_bits((fx - a.w) * irx16));
                         }
                     } else {
                         // Outermost columns: x must lie in [ceil(pdx - r), floor(pdx + r)].  Lanes hold sample s of
@@ -407,7 +409,7 @@ __global__ void __launch_bounds__(TW) splat_window_kernel(SplatParams P) {
                             const float4 a = pa[s];
                             const bool reach = EDGE > 0 ? fx >= a.w - P.rx : fx <= a.w + P.rx;
                             if (!__any_sync(visit_mask, reach)) continue;
-                            taps(a, pb[s], reach ? bin_bits((fx - a.w) * irx16) & 0xFu : (unsigned)TAB_ZERO);
+                            taps(a, pb[s], reach ? bin_bits((fx - a.w) * irx16) : (unsigned)TAB_ZERO);
                         }
                     }
                 };
