@@ -288,6 +288,9 @@ __global__ void __launch_bounds__(TW) splat_window_kernel(SplatParams P) {
 #pragma unroll
     for (int j = 0; j < ROWS; ++j) acc_rg[j] = acc_bw[j] = 0ull;
     unsigned errbits = 0;  // contract violations seen by this thread; reported once at the end
+    float vmax = 0.f, fin = 0.f;  // see the pre-pass
+    const int slot_step = dq * pitch + dr;
+    const float fdq = (float)dq;
     // lanes that gather (the last strip of a row may be narrower than the CTA)
     const unsigned gather_mask = __ballot_sync(0xffffffffu, col_ok);
 
@@ -300,7 +303,11 @@ __global__ void __launch_bounds__(TW) splat_window_kernel(SplatParams P) {
             const float2 *gxy = P.xy + row_base;
             const float4 *grgbw = P.rgbw + row_base;
             const float fny = (float)ny;
-            int q = q0, sidx = r0;
+            // element e of the staged run = (staged pixel q, sample sidx); its record slot and the float of its
+            // pixel coordinate are carried along instead of being recomputed per sample
+            int sidx = r0;
+            int slot = (pl_base + q0) * pitch + r0;
+            float fnx = (float)(sx0 + q0);
             constexpr int U = kPrepassBatch;  // samples per thread per trip: all loads issued before any is consumed
             for (int e0 = tid; e0 < nstaged; e0 += U * TW) {
                 float2 p[U];
@@ -312,38 +319,47 @@ __global__ void __launch_bounds__(TW) splat_window_kernel(SplatParams P) {
                         L[u] = ldg_stream(&grgbw[e0 + u * TW]);
                     }
                 }
+                // WRAP = false when spp divides the strip width: a thread then keeps its sample index for the whole row
+                auto process = [&](auto wrap_tag) {
+                    constexpr bool WRAP = decltype(wrap_tag)::value;
 #pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    if (e0 + u * TW < nstaged) {
-                        const float fnx = (float)(sx0 + q);
-                        if (clamp_on) clamp_luminance(L[u], P.max_lum);
-                        const float cr = L[u].x * L[u].w, cg = L[u].y * L[u].w, cb = L[u].z * L[u].w;
-                        // contract: the sample lies in its nominal pixel (closed) and its radiance is finite
-                        if (!(p[u].x >= fnx && p[u].x <= fnx + 1.f && p[u].y >= fny && p[u].y <= fny + 1.f))
-                            errbits |= ERRBIT_NOT_PIXEL_MAJOR;
-                        if (!(fabsf(cr) + fabsf(cg) + fabsf(cb) < inf)) errbits |= ERRBIT_NONFINITE;
-                        const float pdx = p[u].x - 0.5f, pdy = p[u].y - 0.5f;
-                        unsigned bits[12];
+                    for (int u = 0; u < U; ++u) {
+                        if (e0 + u * TW < nstaged) {
+                            if (clamp_on) clamp_luminance(L[u], P.max_lum);
+                            const float cr = L[u].x * L[u].w, cg = L[u].y * L[u].w, cb = L[u].z * L[u].w;
+                            const float pdx = p[u].x - 0.5f, pdy = p[u].y - 0.5f;
+                            // Contract: the sample lies in its nominal pixel (closed) and everything is finite.  Checked on
+                            // the discrete position every later step uses: |pd - n| <= 0.5; the running maximum and a
+                            // NaN-propagating sum (0 * x is NaN for x = inf or NaN) are tested once at the end.
+                            const float tx = pdx - fnx, ty = pdy - fny;
+                            vmax = fmaxf(vmax, fmaxf(fabsf(tx), fabsf(ty)));
+                            fin = __fmaf_rn(fabsf(cr) + fabsf(cg) + fabsf(cb) + fabsf(tx) + fabsf(ty), 0.f, fin);
+                            unsigned bits[12];
 #pragma unroll
-                        for (int j = 0; j < ROWS; ++j) bits[j] = bin_bits((fny + (float)(j - H) - pdy) * iry16);
+                            for (int j = 0; j < ROWS; ++j) bits[j] = bin_bits((fny + (float)(j - H) - pdy) * iry16);
 #pragma unroll
-                        for (int j = ROWS; j < 12; ++j) bits[j] = 0u;
-                        // only the outermost rows can fall outside [ceil(pdy - r), floor(pdy + r)]
-                        if (!(fny - (float)H >= pdy - P.ry)) bits[0] = TAB_ZERO;
-                        if (!(fny + (float)H <= pdy + P.ry)) bits[ROWS - 1] = TAB_ZERO;
-                        unsigned words[NW];
+                            for (int j = ROWS; j < 12; ++j) bits[j] = 0u;
+                            // only the outermost rows can fall outside [ceil(pdy - r), floor(pdy + r)]
+                            if (!(fny - (float)H >= pdy - P.ry)) bits[0] = TAB_ZERO;
+                            if (!(fny + (float)H <= pdy + P.ry)) bits[ROWS - 1] = TAB_ZERO;
+                            unsigned words[NW];
 #pragma unroll
-                        for (int k = 0; k < NW; ++k)
-                            words[k] = __byte_perm(__byte_perm(bits[4 * k], bits[4 * k + 1], 0x0040),
-                                                   __byte_perm(bits[4 * k + 2], bits[4 * k + 3], 0x0040), 0x5410);
-                        const int slot = (pl_base + q) * pitch + sidx;
-                        s_a[slot] = make_float4(cr, cg, cb, pdx);
-                        rb_make(s_b[slot], words);
+                            for (int k = 0; k < NW; ++k)
+                                words[k] = __byte_perm(__byte_perm(bits[4 * k], bits[4 * k + 1], 0x0040),
+                                                       __byte_perm(bits[4 * k + 2], bits[4 * k + 3], 0x0040), 0x5410);
+                            s_a[slot] = make_float4(cr, cg, cb, pdx);
+                            rb_make(s_b[slot], words);
+                        }
+                        slot += slot_step;
+                        fnx += fdq;
+                        if (WRAP) {
+                            sidx += dr;
+                            if (sidx >= spp) { sidx -= spp; slot += pitch - spp; fnx += 1.f; }
+                        }
                     }
-                    q += dq;
-                    sidx += dr;
-                    if (sidx >= spp) { sidx -= spp; ++q; }
-                }
+                };
+                if (dr == 0) process(std::false_type{});
+                else process(std::true_type{});
             }
             __syncthreads();
             // pull the next sample row of this strip into L2 while this one is gathered, so that its
@@ -435,6 +451,8 @@ __global__ void __launch_bounds__(TW) splat_window_kernel(SplatParams P) {
         for (int j = 0; j + 1 < ROWS; ++j) { acc_rg[j] = acc_rg[j + 1]; acc_bw[j] = acc_bw[j + 1]; }
         acc_rg[ROWS - 1] = acc_bw[ROWS - 1] = 0ull;
     }
+    if (!(vmax <= 0.5f)) errbits |= ERRBIT_NOT_PIXEL_MAJOR;
+    if (fin != fin) errbits |= ERRBIT_NONFINITE;
     if (errbits) atomicOr(P.err, (int)errbits);
 }
 
