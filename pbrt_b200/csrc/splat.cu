@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(256) splat_gather_generic_kernel(SplatParams P
 #define PBRT_WIN_UNROLL 8
 #endif
 #ifndef PBRT_PREPASS_BATCH
-#define PBRT_PREPASS_BATCH 4
+#define PBRT_PREPASS_BATCH 6
 #endif
 constexpr int kPrepassBatch = PBRT_PREPASS_BATCH;
 constexpr int kWinUnroll = PBRT_WIN_UNROLL;
@@ -364,12 +364,14 @@ __global__ void __launch_bounds__(TW) splat_window_kernel(SplatParams P) {
             __syncthreads();
             // pull the next sample row of this strip into L2 while this one is gathered, so that its
             // pre-pass loads pay L2 latency instead of DRAM latency
+#ifndef PBRT_NO_PREFETCH
             if (ny + 1 < P.sb.y1 && ny + 1 < cy1 + H) {
                 const char *nxy = reinterpret_cast<const char *>(gxy + (size_t)W * spp);
                 const char *nrgbw = reinterpret_cast<const char *>(grgbw + (size_t)W * spp);
                 for (int o = tid * 128; o < nstaged * 8; o += TW * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(nxy + o));
                 for (int o = tid * 128; o < nstaged * 16; o += TW * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(nrgbw + o));
             }
+#endif
             // ---------------- gather: this thread's column against the row ----------------
             if (col_ok) {
                 // EDGE = -1 / +1: the outermost columns, whose samples may not reach this pixel; 0: interior
