@@ -13,8 +13,8 @@
 //     A thread owns one pixel COLUMN of a CTA-wide strip and marches down the rows holding a
 //     2h+1-row window of RGBW accumulators in registers.  Per sample row the CTA first runs a
 //     pre-pass, one thread per sample (coalesced float2 + float4 loads): luminance clamp,
-//     L*sample_weight, and the table ROW offset (ify*16) of each of the 2h+1 window rows packed
-//     one per byte (0xFF = row outside the footprint).  Records go to shared memory with a padded
+//     L*sample_weight, and the table ROW (ify) of each of the 2h+1 window rows packed one per byte
+//     (16 = the table's zero row: row outside the footprint).  Records go to shared memory with a padded
 //     pixel pitch so that lanes reading sample s of consecutive pixels hit distinct banks.
 //     The gather then costs, per (sample, column): one LDS.128 + one LDS.32/64, the ifx index
 //     (5 FP ops), and per window row one IDP.4A (table address) + LDS(table) + 3 FMUL + 2 FADD2
@@ -23,6 +23,8 @@
 //     adds packed (tests/test_abi.py checks the SASS).
 //     When the oldest window row can no longer be reached it is converted (rgb_to_xyz) and
 //     added to the film: one float4 read-modify-write per pixel per call.
+//     The kernel is bound by instruction dispatch, not by memory (tools/ubench_gather.cu):
+//     what pays is removing instructions, not hiding latency.
 //
 //   generic gather (any radius): thread per output pixel, samples read through L1/L2.
 //
@@ -35,8 +37,6 @@
 #include <type_traits>
 
 #include "common.cuh"
-
-#include <type_traits>
 
 namespace pb {
 
