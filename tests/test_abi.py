@@ -171,3 +171,13 @@ def test_header_is_valid_c_and_cpp(tmp_path):
     cpp = tmp_path / "t.cpp"
     cpp.write_text('#include "pbrt_b200.hpp"\nint main() { pbrt::Bounds2i b = pbrt::Bounds2i::from({0, 0}, {2, 2}); return b.area() == 4 ? 0 : 1; }\n')
     subprocess.run(["g++", "-std=c++17", "-Wall", "-Werror", "-fsyntax-only", f"-I{ROOT / 'include'}", str(cpp)], check=True)
+
+
+def test_rust_ffi_declares_every_header_symbol():
+    """rust/src/ffi.rs is uncompiled source (no rustc here); at least keep it complete: one `fn` per header symbol."""
+    header = (ROOT / "include" / "pbrt_b200.h").read_text()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    names = set(re.findall(r"\b(pbrt_[a-z0-9_]+)\s*\(", header))
+    ffi = (ROOT / "rust" / "src" / "ffi.rs").read_text()
+    missing = sorted(n for n in names if not re.search(r"\bfn " + n + r"\(", ffi))
+    assert not missing, missing
