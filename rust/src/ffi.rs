@@ -115,6 +115,7 @@ extern "C" {
     pub fn pbrt_film_owned_pixel_bounds(film: *const PbrtFilm, out: *mut i32) -> c_int;
     pub fn pbrt_film_merge_tiles(film: *mut PbrtFilm, ntiles: i32, tile_bounds: *const i32, offsets: *const i64, rgbw: *const c_float, total_pixels: i64, src_is_device: c_int) -> c_int;
     pub fn pbrt_film_add_samples_tiles(film: *mut PbrtFilm, ntiles: i32, sample_bounds: *const i32, sample_offsets: *const i64, spp: i32, xy: *const c_float, rgbw: *const c_float, total_samples: i64, src_is_device: c_int, mode: c_int) -> c_int;
+    pub fn pbrt_film_add_samples(film: *mut PbrtFilm, sample_bounds: *const i32, n: u64, xy: *const c_float, rgbw: *const c_float, src_is_device: c_int) -> c_int;
     pub fn pbrt_film_add_splats(film: *mut PbrtFilm, n: u64, xy: *const c_float, rgb: *const c_float, src_is_device: c_int) -> c_int;
     pub fn pbrt_film_set_image(film: *mut PbrtFilm, rgb: *const c_float, src_is_device: c_int) -> c_int;
     pub fn pbrt_film_clear(film: *mut PbrtFilm) -> c_int;
