@@ -181,3 +181,19 @@ def test_rust_ffi_declares_every_header_symbol():
     ffi = (ROOT / "rust" / "src" / "ffi.rs").read_text()
     missing = sorted(n for n in names if not re.search(r"\bfn " + n + r"\(", ffi))
     assert not missing, missing
+
+
+def test_splat_window_kernels_do_not_spill_and_keep_their_occupancy(pb):
+    """Every splat_window_kernel variant must stay spill-free; the 128-column variants of h <= 3 must stay within
+    the 128 registers that four resident CTAs per SM allow (shared memory admits four: DESIGN.md section 5)."""
+    from pbrt_b200 import _lib
+
+    out = subprocess.run(["cuobjdump", "--dump-resource-usage", str(_lib.LIB_PATH)], capture_output=True, text=True).stdout
+    found = 0
+    for name, regs, local in re.findall(r"Function (\S*splat_window_kernel\S*):\s*\n\s*REG:(\d+) .*?LOCAL:(\d+)", out):
+        found += 1
+        assert int(local) == 0, (name, "spills to local memory")
+        m = re.search(r"ILi(\d)ELi(\d+)ELb", name)
+        if m and int(m.group(2)) == 128 and int(m.group(1)) <= 3:
+            assert int(regs) <= 128, (name, regs)
+    assert found >= 16
