@@ -108,6 +108,8 @@ for _name, (_res, _args) in PROTOTYPES.items():
 # test hook, not part of the public header
 lib.pbrt_b200_debug_force_generic_splat.restype = C.c_int
 lib.pbrt_b200_debug_force_generic_splat.argtypes = [C.c_int]
+lib.pbrt_b200_debug_class_tables.restype = C.c_int
+lib.pbrt_b200_debug_class_tables.argtypes = [_f32p, C.c_float, C.c_float, C.POINTER(C.c_uint8), C.c_int, _i32p]
 
 
 def last_error() -> str:

@@ -16,7 +16,7 @@ ROOT = PKG.parent
 CSRC = PKG / "csrc"
 LIB_DIR = PKG / "lib"
 LIB = LIB_DIR / "libpbrt_b200.so"
-SOURCES = ["film.cu", "splat.cu"]
+SOURCES = ["film.cu", "splat.cu", "splat_class.cu"]
 HEADERS = [CSRC / "common.cuh", CSRC / "to_byte_table.inc", ROOT / "include" / "pbrt_b200.h"]
 
 NVCC_FLAGS = [
@@ -44,18 +44,23 @@ def _stale(out: Path, deps: list[Path]) -> bool:
     return any(d.stat().st_mtime > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> Path:
-    """Compile every .cu for sm_100a and link the shared library. Returns its path."""
+def build(force: bool = False, verbose: bool = False, variant: str = "", defines: list[str] | None = None) -> Path:
+    """Compile every .cu for sm_100a and link the shared library. Returns its path.
+
+    `variant` / `defines` build an experiment copy (lib/libpbrt_b200_<variant>.so with extra -D macros) beside the
+    product library; PBRT_B200_LIB selects which one pbrt_b200/_lib.py loads."""
     LIB_DIR.mkdir(exist_ok=True)
-    objdir = PKG / "build"
-    objdir.mkdir(exist_ok=True)
+    objdir = PKG / "build" / variant if variant else PKG / "build"
+    objdir.mkdir(parents=True, exist_ok=True)
     nvcc = _nvcc()
+    lib = LIB_DIR / f"libpbrt_b200_{variant}.so" if variant else LIB
+    flags = NVCC_FLAGS + [f"-D{d}" for d in (defines or [])]
     objs = []
     for src in SOURCES:
         s = CSRC / src
         o = objdir / (s.stem + ".o")
         if force or _stale(o, [s, *HEADERS, Path(__file__)]):
-            cmd = [nvcc, *NVCC_FLAGS, "-c", str(s), "-o", str(o)]
+            cmd = [nvcc, *flags, "-c", str(s), "-o", str(o)]
             if verbose:
                 cmd.insert(1, "-Xptxas=-v")
             r = subprocess.run(cmd, capture_output=True, text=True)
@@ -64,14 +69,17 @@ def build(force: bool = False, verbose: bool = False) -> Path:
             if r.returncode:
                 raise RuntimeError(f"nvcc failed on {src}")
         objs.append(o)
-    if force or _stale(LIB, objs):
-        cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(LIB), *map(str, objs)]
+    if force or _stale(lib, objs):
+        cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(lib), *map(str, objs)]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode:
             sys.stderr.write(r.stdout + r.stderr)
             raise RuntimeError("link failed")
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    # python pbrt_b200/build.py [--force] [-v] [--variant NAME -DMACRO=V ...]
+    _variant = sys.argv[sys.argv.index("--variant") + 1] if "--variant" in sys.argv else ""
+    _defs = [a[2:] for a in sys.argv if a.startswith("-D")]
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, variant=_variant, defines=_defs))

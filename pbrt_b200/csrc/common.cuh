@@ -119,6 +119,11 @@ struct PbrtFilm {
     cudaEvent_t ev_staged[2], ev_consumed[2];
     bool pipe_ready;
     int pipe_turn;
+    // splat_class.cu: phase-class tables of the filter (LUTs + precombined weight blocks), built when the radius is
+    // 1, 2 or 4 on both axes; class_bytes == 0 otherwise
+    void *d_class;
+    int class_bytes;
+    int class_h, class_k, class_rowp;
 };
 
 namespace pb {
@@ -158,10 +163,35 @@ struct SplatTile {
     long long pixel_offset;   // first pixel of the tile in the RGBW scratch buffer
 };
 
+// arguments of the pixel-major splat kernels (splat.cu, splat_class.cu)
+struct SplatParams {
+    Bounds sb;      // sample bounds (nominal pixels that carry samples)
+    Bounds tb;      // tile pixel bounds = get_film_tile(sb), already clipped to the film
+    Bounds owned;   // film rows/cols stored
+    int spp;
+    float rx, ry, irx, iry;
+    float max_lum;
+    const float2 *xy;
+    const float4 *rgbw;
+    const float *table;  // 256 floats, device
+    float4 *film;
+    int *err;
+    int rows_per_cta;
+    // batched mode (pbrt_film_add_samples_tiles): blockIdx.z selects a tile; its bounds and streams replace
+    // sb / tb / xy / rgbw, and finished pixels go to the tile's own RGBW buffer instead of the film
+    const SplatTile *tiles;
+    float4 *tile_out;
+};
+
 // kernels implemented in splat.cu
 int launch_splat_tiles(PbrtFilm *f, int ntiles, const SplatTile *d_tiles, int max_w, int max_h, int spp, const float2 *xy,
                        const float4 *rgbw, float4 *tile_out, int mode);
 int launch_splat_tile(PbrtFilm *f, const Bounds &sb, const Bounds &tb, int spp, const float2 *xy, const float4 *rgbw,
                       int mode);
+
+// splat_class.cu: the phase-class gather (radius 1, 2 or 4).  class_tables_create uploads the tables of f->table
+// (no-op for other radii); launch_splat_class returns -1 when the film / stream shape is not one it serves.
+int class_tables_create(PbrtFilm *f);
+int launch_splat_class(PbrtFilm *f, const SplatParams &P, int mode);
 
 }  // namespace pb

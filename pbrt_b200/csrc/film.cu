@@ -359,8 +359,9 @@ static int film_create_impl(int32_t xres, int32_t yres, const float crop[4], con
     if (e == cudaSuccess) e = cudaMalloc(&f->d_err, sizeof(int));
     if (e != cudaSuccess) {
         cudaGetLastError();
+        const long long npix = (long long)f->npix;
         pbrt_film_destroy(f);
-        return e == cudaErrorMemoryAllocation ? fail(PBRT_E_NOMEM, "film of %lld pixels does not fit", (long long)f->npix)
+        return e == cudaErrorMemoryAllocation ? fail(PBRT_E_NOMEM, "film of %lld pixels does not fit", npix)
                                               : pb::cuda_fail(e, "film alloc");
     }
     cudaStream_t s = ctx().stream;
@@ -369,6 +370,10 @@ static int film_create_impl(int32_t xres, int32_t yres, const float crop[4], con
     PB_CUDA(cudaMemsetAsync(f->d_err, 0, sizeof(int), s));
     PB_CUDA(cudaMemcpyAsync(f->d_table, f->table, sizeof f->table, cudaMemcpyHostToDevice, s));
     PB_CUDA(cudaStreamSynchronize(s));
+    if (int rc = pb::class_tables_create(f)) {
+        pbrt_film_destroy(f);
+        return rc;
+    }
     *out = f;
     return PBRT_OK;
 }
@@ -398,6 +403,7 @@ extern "C" int pbrt_film_destroy(PbrtFilm *f) {
     cudaFree(f->d_scratch_tile);
     cudaFree(f->d_idx);
     cudaFree(f->d_tile_desc);
+    cudaFree(f->d_class);
     for (int i = 0; i < 2; ++i) {
         for (int k = 0; k < 4; ++k) cudaFree(f->d_pipe[i][k]);
         if (f->pipe_ready) { cudaEventDestroy(f->ev_staged[i]); cudaEventDestroy(f->ev_consumed[i]); }

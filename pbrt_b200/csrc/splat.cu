@@ -40,24 +40,6 @@
 
 namespace pb {
 
-struct SplatParams {
-    Bounds sb;      // sample bounds (nominal pixels that carry samples)
-    Bounds tb;      // tile pixel bounds = get_film_tile(sb), already clipped to the film
-    Bounds owned;   // film rows/cols stored
-    int spp;
-    float rx, ry, irx, iry;
-    float max_lum;
-    const float2 *xy;
-    const float4 *rgbw;
-    const float *table;  // 256 floats, device
-    float4 *film;
-    int *err;
-    int rows_per_cta;
-    // batched mode (pbrt_film_add_samples_tiles): blockIdx.z selects a tile; its bounds and streams replace
-    // sb / tb / xy / rgbw, and finished pixels go to the tile's own RGBW buffer instead of the film
-    const SplatTile *tiles;
-    float4 *tile_out;
-};
 
 
 // ---- pieces shared by all variants -------------------------------------------------------
@@ -693,6 +675,11 @@ int launch_splat_tile(PbrtFilm *f, const Bounds &sb, const Bounds &tb, int spp, 
     }
 
     const bool fma = mode == PBRT_SPLAT_FMA;
+    if (!g_force_generic) {
+        // radius 2 or 4: the phase-class gather (splat_class.cu); -1 = not served, fall through
+        int rc = launch_splat_class(f, P, mode);
+        if (rc >= 0) return rc;
+    }
     if (!g_force_generic && hx == hy && hx >= 1 && hx <= 4) {
         int rc = fma ? pick_window<true>(P, hx) : pick_window<false>(P, hx);
         if (rc >= 0) return rc;

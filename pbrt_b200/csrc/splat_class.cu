@@ -1,0 +1,730 @@
+// splat_class.cu — [T2, extension] the phase-class gather: FilmTile::add_sample for a pixel-major stream when the
+// filter radius is 2 or 4 pixels on both axes (the radii of triangle / gaussian / mitchell and of lanczos-sinc).
+// Same contract and the same results, bit for bit, as splat_window_kernel (splat.cu) and the CPU restatement
+// (oracle/pbrt_oracle.c:orc_ext_tile_add_sample, pbrt-v3 7.9.2 over the fields at src/core/film.rs:428-436).
+//
+// Why it is faster.  The window gather is bound by instruction dispatch: per (sample, pixel) tap it
+// pays a table-address IDP and an LDS, per (sample, column) visit five instructions for the table column, and it
+// computes every row of the 2h+1 window although a sample reaches only 2h of them.  All of that is a function of the
+// sample's sub-pixel PHASE w = (p - 0.5) - nominal pixel, in [-0.5, 0.5], and for an integer radius r the function is a
+// step function with few steps: with K = 16 / r table cells per pixel, every table index floor(|(d - w) * K|) is constant
+// on each of the K open intervals between the points m / K - 0.5, and takes its own values on those K + 1 points.
+// So the pre-pass classifies the phase on each axis once per sample (2K + 1 classes: one LUT fetch and two comparisons
+// against float bounds the host found by bisection over the very float expression the CPU path evaluates), and the
+// record carries the shared-memory address of the class pair's block of PRECOMBINED weights
+//        block[column d][row i] = table[ify(i)][ifx(d)],  2h live rows per column, zero for an unreached column.
+// The gather then costs, per (sample, column): LDS.128 record + LDS.128 weights (two at h = 4) and per live row
+// 3 FMUL + 2 FADD2 — no index arithmetic, no per-tap load, no dead row.  Which 2h of the 2h+1 window rows are live
+// ("up": rows 0..2h-1, phase < 0; "down": rows 1..2h, phase > 0, stored mirrored) and whether an outermost column is
+// reached are properties of the class; the pre-pass reduces them over the strip to one bit per sample index, and the
+// gather walks runs of sample indices that are uniformly "up" or "down" with branch-free bodies (stratified streams:
+// two runs).  Anything else — a phase exactly 0 (2h+1 live rows), a sample whose floor(pd + r) rounds across an
+// integer at a power-of-two coordinate, a stream that is not stratified — goes through a per-lane general body, and a
+// sample no class describes through a slow path that evaluates the CPU expressions directly.  Nothing is approximated.
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <type_traits>
+#include <vector>
+
+#include "common.cuh"
+
+namespace pb {
+
+// ---- table geometry (host and device) ------------------------------------------------------------------------------
+
+// Two LUTs per axis, indexed by a phase cell.
+//   fast    cell = floor(K * (w + 0.5)), entry {point, offset(interval), offset(point)}: valid when the phase is a multiple
+//           of 2^-22 (any sample with |pd| >= 2): every d - w is then exact and the classes are the ideal ones —
+//           the single float `point` and the open interval above it.
+//   careful cell = nearest point, entry {glo, ghi, point, -, offset(interval below), offset(point), offset(interval above)}:
+//           for the pixels next to the origin, where a finer-grained phase within a few ulps of a point rounds
+//           differently in d - w for different d.  [glo, ghi] is the range around the point outside of which the
+//           neighbouring interval's profile holds; inside it only the point itself is a class.
+constexpr int CT_LUT_ENTRIES = 32;                 // fast cells; entries above K are empty
+constexpr int CT_LUT_BYTES = CT_LUT_ENTRIES * 16;
+constexpr int CT_CARE_ENTRIES = 16;
+constexpr int CT_CARE_BYTES = CT_CARE_ENTRIES * 32;
+constexpr int CT_LUT_Y = 0, CT_LUT_X = CT_LUT_BYTES;
+constexpr int CT_CARE_Y = 2 * CT_LUT_BYTES, CT_CARE_X = CT_CARE_Y + CT_CARE_BYTES;
+constexpr int CT_Q_OFFSET = CT_CARE_X + CT_CARE_BYTES;
+// an offset no class has: the sample takes the slow path (x and y markers add without cancelling)
+constexpr unsigned CT_SLOW_X = 0x40000000u, CT_SLOW_Y = 0x80000000u;
+constexpr int CT_ZERO = 16;  // "not reached" in a profile
+// flag bits in the low nibble of a LUT offset (block addresses are multiples of 16)
+constexpr unsigned CF_DOWN = 1, CF_BOTH = 2, CF_LEFT = 4, CF_RIGHT = 8, CF_SLOW = 15;
+
+template <int H> struct ClassCfg {
+    static constexpr int ROWS = 2 * H + 1;
+    static constexpr int LIVE = 2 * H;
+    static constexpr int K = 16 / H;
+    static constexpr int NX = 2 * K + 1;
+    static constexpr int COLB = LIVE * 4;    // bytes per column of a block
+    static constexpr int BLK = ROWS * COLB;  // bytes per class-pair block
+};
+
+struct ClassGeom {
+    int H, K, NX, NXP, COLB, BLK, ROWP, EOFF, BYTES;
+};
+
+static bool class_geom(float rx, float ry, ClassGeom *g) {
+    if (rx != ry || (rx != 2.f && rx != 4.f)) return false;
+    g->H = (int)rx;
+    g->K = 16 / g->H;
+    g->NX = 2 * g->K + 1;
+    g->COLB = 2 * g->H * 4;
+    g->BLK = (2 * g->H + 1) * g->COLB;
+    // Row pitch in blocks.  The lanes of a warp hold sample s of neighbouring pixels; for a stratified stream they fall into
+    // a few neighbouring classes on each axis.  A pitch whose 16-byte count is 2 or 6 modulo 8 puts the four interval
+    // classes of such a neighbourhood on four different bank groups.
+    g->NXP = g->NX;
+    for (int n = g->NX; n < g->NX + 8; ++n)
+        if (((n * g->BLK / 16) % 8) == 2 || ((n * g->BLK / 16) % 8) == 6) { g->NXP = n; break; }
+    g->ROWP = g->NXP * g->BLK;
+    g->EOFF = CT_Q_OFFSET + (g->K + 1) * g->ROWP;  // last-row weights of the phase-0 class: [class x][column]
+    g->BYTES = (g->EOFF + g->NX * (2 * g->H + 1) * 4 + 15) / 16 * 16;
+    return true;
+}
+
+// ---- host: profiles, classes, tables -----------------------------------------------------------------------------
+
+// One axis of add_sample for a sample of phase w: for pixel offset d in -H..H the filter-table index the CPU path
+// computes — min(floor(|((x - pd) * inv_radius) * 16|), 15) with x - pd == d - w exactly, the scaling by 16 / r a power
+// of two — or CT_ZERO when [ceil(pd - r), floor(pd + r)] excludes the pixel (in exact arithmetic; the kernel checks
+// the one place where the float expression can differ, see class_prepass).
+static void axis_profile(float w, int H, int *bins) {
+    const float c16 = (1.f / (float)H) * 16.f;
+    for (int d = -H; d <= H; ++d) {
+        const bool reached = d == -H ? w <= 0.f : (d == H ? w >= 0.f : true);
+        const float t = fabsf(((float)d - w) * c16);
+        int b = t >= 16.f ? 15 : (int)floorf(t);
+        if (b > 15) b = 15;
+        bins[d + H] = reached ? b : CT_ZERO;
+    }
+}
+
+static int32_t float_order(float f) {
+    int32_t i;
+    memcpy(&i, &f, 4);
+    return i ^ ((i >> 31) & 0x7fffffff);
+}
+static float order_float(int32_t o) {
+    int32_t i = o ^ ((o >> 31) & 0x7fffffff);
+    float f;
+    memcpy(&f, &i, 4);
+    return f;
+}
+
+static float class_point(int kk, int K) { return (float)kk / (float)K - 0.5f; }
+static float class_mid(int kk, int K) { return ((float)kk + 0.5f) / (float)K - 0.5f; }
+// representative phase of class c (even: the point c/2, odd: the interval (c-1)/2)
+static float class_rep(int c, int K) { return (c & 1) ? class_mid(c >> 1, K) : class_point(c >> 1, K); }
+
+// Builds the blob the kernel copies into shared memory: two LUTs and the weight blocks.  Returns false when the radius is
+// not served or the float step function does not have the expected shape (then the window kernel runs instead).
+static bool class_tables_host(const float table[256], float rx, float ry, std::vector<unsigned char> *blob,
+                              ClassGeom *geom) {
+    ClassGeom g;
+    if (!class_geom(rx, ry, &g)) return false;
+    const int H = g.H, K = g.K, ROWS = 2 * H + 1;
+    std::vector<int> want(ROWS), prof(ROWS);
+    auto same = [&](float w) {
+        axis_profile(w, H, prof.data());
+        return std::equal(prof.begin(), prof.end(), want.begin());
+    };
+    // first float from `good` towards `bad` (both in float order) whose profile is still `want`
+    auto boundary = [&](float bad, float good) {
+        int32_t a = float_order(bad), b = float_order(good);
+        const int32_t step = a < b ? 1 : -1;
+        while ((b - a) * step > 1) {
+            const int32_t m = a + (b - a) / 2;
+            if (same(order_float(m))) b = m; else a = m;
+        }
+        return order_float(b);
+    };
+    // interval kk = [ilo, ihi]: every float in it has the profile of the interval's midpoint
+    std::vector<float> ilo(K), ihi(K);
+    const float grain = 1.f / 4194304.f;  // 2^-22
+    for (int kk = 0; kk < K; ++kk) {
+        axis_profile(class_mid(kk, K), H, want.data());
+        ilo[kk] = boundary(class_point(kk, K), class_mid(kk, K));
+        ihi[kk] = boundary(class_point(kk + 1, K), class_mid(kk, K));
+        // the fast LUT's premise: on the 2^-22 grid the interval is everything strictly between its two points
+        if (!(ilo[kk] <= class_point(kk, K) + grain && ihi[kk] >= class_point(kk + 1, K) - grain)) return false;
+    }
+    // "down" classes are stored as their mirror image: profile(w) reversed must be profile(-w)
+    for (int c = 0; c <= 2 * K; ++c) {
+        std::vector<int> a(ROWS), b(ROWS);
+        axis_profile(class_rep(c, K), H, a.data());
+        axis_profile(class_rep(2 * K - c, K), H, b.data());
+        std::reverse(b.begin(), b.end());
+        if (a != b) return false;
+    }
+    blob->assign(g.BYTES, 0);
+    auto offx = [&](int c) { return (uint32_t)(c * g.BLK) | (c <= K ? CF_LEFT : 0u) | (c >= K ? CF_RIGHT : 0u); };
+    auto offy = [&](int c) {
+        const int row = c <= K ? c : 2 * K - c;
+        return (uint32_t)(CT_Q_OFFSET + row * g.ROWP) | (c > K ? CF_DOWN : 0u) | (c == K ? CF_BOTH : 0u);
+    };
+    struct Fast { float point; uint32_t off_interval, off_point, pad; };
+    struct Care { float glo, ghi, point, pad0; uint32_t off_below, off_point, off_above, pad1; };
+    for (int axis = 0; axis < 2; ++axis) {
+        const uint32_t slow = axis ? CT_SLOW_X : CT_SLOW_Y;
+        auto off = [&](int c) { return axis ? offx(c) : offy(c); };
+        Fast *fast = reinterpret_cast<Fast *>(blob->data() + (axis ? CT_LUT_X : CT_LUT_Y));
+        for (int kk = 0; kk < CT_LUT_ENTRIES; ++kk) {
+            Fast e = {NAN, slow, slow, 0u};
+            if (kk <= K) {
+                e.point = class_point(kk, K);
+                e.off_point = off(2 * kk);
+                if (kk < K) e.off_interval = off(2 * kk + 1);
+            }
+            fast[kk] = e;
+        }
+        Care *care = reinterpret_cast<Care *>(blob->data() + (axis ? CT_CARE_X : CT_CARE_Y));
+        for (int m = 0; m < CT_CARE_ENTRIES; ++m) {
+            Care e = {INFINITY, -INFINITY, NAN, 0.f, slow, slow, slow, 0u};  // w < glo: slow
+            if (m <= K) {
+                e.point = class_point(m, K);
+                e.off_point = off(2 * m);
+                // below the point: interval m-1 up to its last float; above: interval m from its first float
+                e.glo = m > 0 ? order_float(float_order(ihi[m - 1]) + 1) : e.point;
+                e.ghi = m < K ? order_float(float_order(ilo[m]) - 1) : e.point;
+                if (m > 0) e.off_below = off(2 * m - 1);
+                if (m < K) e.off_above = off(2 * m + 1);
+            }
+            care[m] = e;
+        }
+    }
+    std::vector<int> px(ROWS), py(ROWS);
+    for (int cy = 0; cy <= K; ++cy) {
+        axis_profile(class_rep(cy, K), H, py.data());
+        for (int cx = 0; cx <= 2 * K; ++cx) {
+            axis_profile(class_rep(cx, K), H, px.data());
+            for (int v = 0; v < ROWS; ++v) {
+                auto weight = [&](int i) {
+                    return (px[v] == CT_ZERO || py[i] == CT_ZERO) ? 0.f : table[py[i] * 16 + px[v]];
+                };
+                float *col = reinterpret_cast<float *>(blob->data() + CT_Q_OFFSET + cy * g.ROWP + cx * g.BLK + v * g.COLB);
+                for (int i = 0; i < 2 * H; ++i) col[i] = weight(i);
+                if (cy == K) reinterpret_cast<float *>(blob->data() + g.EOFF)[cx * ROWS + v] = weight(2 * H);
+            }
+        }
+    }
+    *geom = g;
+    return true;
+}
+
+int class_tables_create(PbrtFilm *f) {
+    std::vector<unsigned char> blob;
+    ClassGeom g;
+    f->class_bytes = 0;
+    if (!class_tables_host(f->table, f->radius[0], f->radius[1], &blob, &g)) return PBRT_OK;
+    PB_CUDA(cudaMalloc(&f->d_class, blob.size()));
+    PB_CUDA(cudaMemcpyAsync(f->d_class, blob.data(), blob.size(), cudaMemcpyHostToDevice, ctx().stream));
+    PB_CUDA(cudaStreamSynchronize(ctx().stream));  // blob is a local
+    f->class_bytes = (int)blob.size();
+    f->class_h = g.H;
+    f->class_k = g.K;
+    f->class_rowp = g.ROWP;
+    return PBRT_OK;
+}
+
+// ---- device ----------------------------------------------------------------------------------------------------
+
+typedef unsigned long long u64;
+
+struct ClassParams {
+    SplatParams S;
+    const uint4 *blob;
+    int blob_bytes;
+    int rowp;
+    int eoff;
+};
+
+__device__ __forceinline__ u64 cpack2(float lo, float hi) {
+    u64 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void cunpack2(u64 v, float &lo, float &hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ u64 cadd2(u64 a, u64 b) {
+    u64 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+// Loads from the table blob, which is constant once the barrier after its fill has passed.  Not volatile: the address
+// depends on data read after that barrier, so the compiler may schedule these freely across the unrolled samples.
+__device__ __forceinline__ void lds_blob4(unsigned addr, float &a, float &b, float &c, float &d) {
+    asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(a), "=f"(b), "=f"(c), "=f"(d) : "r"(addr));
+}
+// record / flag stores by shared-window address (a generic pointer makes the compiler rebuild the window base per store)
+__device__ __forceinline__ void sts_rec(unsigned addr, float a, float b, float c, unsigned d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void sts_flag(unsigned addr, unsigned v) {
+    asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ float lds_blob1(unsigned addr) {
+    float v;
+    asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+
+// min(floor(|v|), 15) — the CPU path's table index (slow path only)
+__device__ __forceinline__ int class_table_index(float v) {
+    return __float_as_int(__fadd_rd(fminf(fabsf(v), 15.f), 8388608.f)) & 0xF;
+}
+
+// Window accumulators: ROWS x {r, g, b, weight}.  LAYOUT 0: two packed pairs (r,g) (b,w) per row, sums by FADD2 — the
+// (b*w, w) addend pair costs a MOV per tap since w arrives in a register of its own; 1: (r,g) packed, b and w scalar;
+// 2: four scalars.  The fused variant (PBRT_SPLAT_FMA) always uses 2.  Indices are compile-time after unrolling.
+#ifndef PBRT_CLASS_ACC
+#define PBRT_CLASS_ACC 1
+#endif
+template <int ROWS, int LAYOUT>
+struct ClassAcc {
+    u64 rg[LAYOUT <= 1 ? ROWS : 1];
+    u64 bw[LAYOUT == 0 ? ROWS : 1];
+    float r[LAYOUT == 2 ? ROWS : 1], g[LAYOUT == 2 ? ROWS : 1];
+    float b[LAYOUT >= 1 ? ROWS : 1], w[LAYOUT >= 1 ? ROWS : 1];
+    __device__ __forceinline__ void clear(const int j) {
+        if (LAYOUT <= 1) rg[j] = 0ull; else r[j] = g[j] = 0.f;
+        if (LAYOUT == 0) bw[j] = 0ull; else b[j] = w[j] = 0.f;
+    }
+    __device__ __forceinline__ void move(const int to, const int from) {
+        if (LAYOUT <= 1) rg[to] = rg[from]; else { r[to] = r[from]; g[to] = g[from]; }
+        if (LAYOUT == 0) bw[to] = bw[from]; else { b[to] = b[from]; w[to] = w[from]; }
+    }
+    __device__ __forceinline__ void get(const int j, float &R, float &G, float &B, float &Wt) const {
+        if (LAYOUT <= 1) cunpack2(rg[j], R, G); else { R = r[j]; G = g[j]; }
+        if (LAYOUT == 0) cunpack2(bw[j], B, Wt); else { B = b[j]; Wt = w[j]; }
+    }
+    // exact: products by scalar multiplies (rounded like the CPU's), then added — ptxas would fuse a packed multiply
+    // feeding a packed add into one FFMA2 even under --fmad=false
+    __device__ __forceinline__ void tap(const int j, const float cr, const float cg, const float cb, const float wt) {
+        if (LAYOUT <= 1) rg[j] = cadd2(rg[j], cpack2(cr * wt, cg * wt));
+        else { r[j] += cr * wt; g[j] += cg * wt; }
+        if (LAYOUT == 0) bw[j] = cadd2(bw[j], cpack2(cb * wt, wt));
+        else { b[j] += cb * wt; w[j] += wt; }
+    }
+    // same order, one rounding per accumulate (LAYOUT 2 only)
+    __device__ __forceinline__ void tap_fma(const int j, const float cr, const float cg, const float cb, const float wt) {
+        r[j] = __fmaf_rn(cr, wt, r[j]); g[j] = __fmaf_rn(cg, wt, g[j]); b[j] = __fmaf_rn(cb, wt, b[j]);
+        w[j] += wt;
+    }
+};
+
+template <int H, int TW>
+struct ClassSmem {
+    static constexpr int NPX = TW + 2 * H;
+    static constexpr int MASK_BYTES = 64;  // 2 parities x 6 words, padded
+    __host__ __device__ static int pitch(int spp) { return spp | 1; }
+    __host__ __device__ static size_t bytes(int blob_bytes, int spp) {
+        return (size_t)blob_bytes + MASK_BYTES + ((size_t)NPX * pitch(spp) * 17 + 15) / 16 * 16;
+    }
+};
+
+#ifndef PBRT_CLASS_PREPASS_BATCH
+#define PBRT_CLASS_PREPASS_BATCH 6
+#endif
+#ifndef PBRT_CLASS_UNROLL
+#define PBRT_CLASS_UNROLL 4
+#endif
+constexpr int kClassUnroll = PBRT_CLASS_UNROLL;  // samples per trip of a run's loop
+
+template <int H, int TW, bool FMA>
+__global__ void __launch_bounds__(TW, 512 / TW) splat_class_kernel(ClassParams CP) {
+    typedef ClassCfg<H> C;
+    constexpr int ROWS = C::ROWS, LIVE = C::LIVE, K = C::K, COLB = C::COLB, BLK = C::BLK;
+    constexpr int NPX = ClassSmem<H, TW>::NPX;
+    const SplatParams &P = CP.S;
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int tid = threadIdx.x;
+    const int spp = P.spp;
+    const int pitch = ClassSmem<H, TW>::pitch(spp);
+    unsigned *s_mask = reinterpret_cast<unsigned *>(smem + CP.blob_bytes);
+    float4 *s_rec = reinterpret_cast<float4 *>(smem + CP.blob_bytes + ClassSmem<H, TW>::MASK_BYTES);
+    unsigned char *s_flag = reinterpret_cast<unsigned char *>(s_rec + (size_t)NPX * pitch);
+
+    for (int i = tid; i < CP.blob_bytes / 16; i += TW) reinterpret_cast<uint4 *>(smem)[i] = CP.blob[i];
+    if (tid < ClassSmem<H, TW>::MASK_BYTES / 4) s_mask[tid] = 0u;
+    __syncthreads();
+    // shared-window address of the blob, kept opaque so that it lives in a register
+    unsigned sbase = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("mov.u32 %0, %0;" : "+r"(sbase));
+    const unsigned a_rec = sbase + CP.blob_bytes + ClassSmem<H, TW>::MASK_BYTES;
+    const unsigned a_flag = a_rec + (unsigned)(NPX * pitch) * 16u;
+
+    const int cx0 = P.tb.x0 + blockIdx.x * TW;              // first output column of the strip
+    const int cy0 = P.tb.y0 + blockIdx.y * P.rows_per_cta;  // first output row
+    const int cy1 = min(cy0 + P.rows_per_cta, P.tb.y1);
+    const int x = cx0 + tid;
+    const bool col_ok = x < P.tb.x1;
+    const float fx = (float)x;
+    const int W = P.sb.x1 - P.sb.x0;
+    const bool clamp_on = P.max_lum < __int_as_float(0x7f800000);
+    const float rH = (float)H;                 // == P.rx == P.ry
+    const float c16 = (1.f / rH) * 16.f;       // inv_radius * 16, exact
+
+    // staged nominal pixels of a row: [sx0, sx1); local index = nx - (cx0 - H)
+    const int sx0 = max(cx0 - H, P.sb.x0), sx1 = min(cx0 + TW + H, P.sb.x1);
+    const int nstaged = max(sx1 - sx0, 0) * spp;
+    // element e = tid + k*TW of the staged run is sample `sidx` of staged pixel q: advance (q, sidx) without dividing
+    const int q0 = tid / spp, r0 = tid - q0 * spp;
+    const int dq = TW / spp, dr = TW - dq * spp;
+    const int pl_base = sx0 - (cx0 - H);
+    const int slot_step = dq * pitch + dr;
+    const float fdq = (float)dq;
+    // a thread keeps its sample index for the whole row when spp divides the strip width: the per-index class masks
+    // are then reduced in registers; otherwise (and above 32 spp) every sample takes the general body
+    const bool mask_mode = dr == 0 && spp <= 32;
+    const unsigned sppmask = spp >= 32 ? 0xffffffffu : ((1u << spp) - 1u);
+
+    ClassAcc<ROWS, FMA ? 2 : PBRT_CLASS_ACC> acc;
+#pragma unroll
+    for (int j = 0; j < ROWS; ++j) acc.clear(j);
+    unsigned errbits = 0;
+    float vmax = 0.f;  // largest |phase| this thread has seen
+    int parity = 0;
+
+    auto tap = [&](const int j, const float cr, const float cg, const float cb, const float w) {
+        if (FMA) acc.tap_fma(j, cr, cg, cb, w);
+        else acc.tap(j, cr, cg, cb, w);
+    };
+
+    for (int ny = cy0 - H; ny < cy1 + H; ++ny) {
+        const bool row_has_samples = ny >= P.sb.y0 && ny < P.sb.y1 && nstaged > 0;
+        if (row_has_samples) {
+            __syncthreads();  // previous row fully consumed
+            // ---------------- pre-pass: one thread per sample of the row ----------------
+            const size_t row_base = ((size_t)(ny - P.sb.y0) * W + (sx0 - P.sb.x0)) * (size_t)spp;
+            const float2 *gxy = P.xy + row_base;
+            const float4 *grgbw = P.rgbw + row_base;
+            const float fny = (float)ny, fnyH = fny + rH;
+            const bool hazard_y = fabsf(fny) < 2.5f;
+            int sidx = r0;
+            int slot = (pl_base + q0) * pitch + r0;
+            float fnx = (float)(sx0 + q0);
+            unsigned andf = 15u, orf = 0u;
+            constexpr int U = PBRT_CLASS_PREPASS_BATCH;
+            for (int e0 = tid; e0 < nstaged; e0 += U * TW) {
+                float2 p[U];
+                float4 L[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    if (e0 + u * TW < nstaged) {
+                        p[u] = ldg_stream(&gxy[e0 + u * TW]);
+                        L[u] = ldg_stream(&grgbw[e0 + u * TW]);
+                    }
+                }
+                if (clamp_on) {  // max_sample_luminance, off (infinite) in every BASELINE config: kept out of the main body
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        if (e0 + u * TW < nstaged) {
+                            const float ly = luminance(L[u].x, L[u].y, L[u].z);
+                            if (ly > P.max_lum) {
+                                const float sc = P.max_lum / ly;
+                                L[u].x *= sc; L[u].y *= sc; L[u].z *= sc;
+                            }
+                        }
+                    }
+                }
+                auto process = [&](auto wrap_tag) {
+                    constexpr bool WRAP = decltype(wrap_tag)::value;
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        if (e0 + u * TW < nstaged) {
+                            const float cr = L[u].x * L[u].w, cg = L[u].y * L[u].w, cb = L[u].z * L[u].w;
+                            const float pdx = p[u].x - 0.5f, pdy = p[u].y - 0.5f;
+                            // phase: exact (Sterbenz) for a sample inside its nominal pixel
+                            const float wx = pdx - fnx, wy = pdy - fny;
+                            // contract: the sample lies in its nominal pixel (a NaN phase reaches the slow path instead)
+                            vmax = fmaxf(vmax, fmaxf(fabsf(wx), fabsf(wy)));
+                            unsigned offx, offy;
+                            if (!(hazard_y || fabsf(fnx) < 2.5f)) {
+                                // |pd| >= 2: the phase is a multiple of 2^-22, the classes are the ideal ones
+                                auto classify = [&](const float w, const unsigned lut) {
+                                    float t = __fmaf_rn(w, (float)K, 0.5f * (float)K);
+                                    t = fminf(fabsf(t), (float)(CT_LUT_ENTRIES - 1));
+                                    const unsigned cell = (unsigned)__float_as_int(__fadd_rd(t, 8388608.f));
+                                    float point, oi, op, pad;
+                                    lds_blob4(__dp4a(cell, 16u, lut), point, oi, op, pad);
+                                    return __float_as_uint(w == point ? op : oi);
+                                };
+                                offx = classify(wx, sbase + CT_LUT_X);
+                                offy = classify(wy, sbase + CT_LUT_Y);
+                            } else {
+                                // next to the origin the phase can be finer than 2^-22: bounds found on the host decide
+                                auto classify = [&](const float w, const unsigned lut, const unsigned slow) {
+                                    float t = __fmaf_rn(w, (float)K, 0.5f * (float)K + 0.5f);
+                                    t = fminf(fabsf(t), (float)(CT_CARE_ENTRIES - 1));
+                                    const unsigned cell = (unsigned)__float_as_int(__fadd_rd(t, 8388608.f));
+                                    const unsigned e = __dp4a(cell, 32u, lut);
+                                    float glo, ghi, point, pad0, ob, op, oa, pad1;
+                                    lds_blob4(e, glo, ghi, point, pad0);
+                                    lds_blob4(e + 16, ob, op, oa, pad1);
+                                    return w < glo ? __float_as_uint(ob)
+                                                   : (w > ghi ? __float_as_uint(oa) : (w == point ? __float_as_uint(op) : slow));
+                                };
+                                offx = classify(wx, sbase + CT_CARE_X, CT_SLOW_X);
+                                offy = classify(wy, sbase + CT_CARE_Y, CT_SLOW_Y);
+                            }
+                            // The classes take "pixel n + H is reached" to mean w >= 0.  The CPU path asks whether
+                            // n + H <= floor(pd + r) in floats, and pd + r can round up to the integer when it crosses a
+                            // power of two: such a sample is none of the classes.  (ceil(pd - r) has no such case: the
+                            // difference is exact wherever the result is a pixel coordinate >= 0.)
+                            const bool ok = offx + offy < CT_SLOW_X && !(wx < 0.f && fnx + rH <= pdx + rH) &&
+                                            !(wy < 0.f && fnyH <= pdy + rH);
+                            const unsigned sum = offx + offy;
+                            const unsigned fl = ok ? (sum & 15u) : CF_SLOW;
+                            const unsigned meta = (sbase + sum) & ~15u;
+                            sts_rec(a_rec + 16u * (unsigned)slot, cr, cg, cb, meta);
+                            sts_flag(a_flag + (unsigned)slot, fl);
+                            andf &= fl;
+                            orf |= fl;
+                        }
+                        slot += slot_step;
+                        fnx += fdq;
+                        if (WRAP) {
+                            sidx += dr;
+                            if (sidx >= spp) { sidx -= spp; slot += pitch - spp; fnx += 1.f; }
+                        }
+                    }
+                };
+                if (dr == 0) process(std::false_type{});
+                else process(std::true_type{});
+            }
+            // per sample index: is every sample of the strip "up" / "down", does every / no sample reach the outermost
+            // column on the left / right.  Words: 0 !up 1 !down 2 !left-all 3 !left-none 4 !right-all 5 !right-none
+            unsigned *mk = s_mask + parity * 8;
+            if (mask_mode && tid < nstaged) {
+                const unsigned bit = 1u << r0;
+                if (orf & 3u) atomicOr(&mk[0], bit);
+                if (!(andf & CF_DOWN) || (orf & CF_BOTH)) atomicOr(&mk[1], bit);
+                if (!(andf & CF_LEFT)) atomicOr(&mk[2], bit);
+                if (orf & CF_LEFT) atomicOr(&mk[3], bit);
+                if (!(andf & CF_RIGHT)) atomicOr(&mk[4], bit);
+                if (orf & CF_RIGHT) atomicOr(&mk[5], bit);
+            }
+            __syncthreads();
+            if (tid < 8) s_mask[(parity ^ 1) * 8 + tid] = 0u;  // last read before this row's first barrier
+            // pull the next sample row of this strip into L2 while this one is gathered
+#ifndef PBRT_NO_PREFETCH
+            if (ny + 1 < P.sb.y1 && ny + 1 < cy1 + H) {
+                const char *nxy = reinterpret_cast<const char *>(gxy + (size_t)W * spp);
+                const char *nrgbw = reinterpret_cast<const char *>(grgbw + (size_t)W * spp);
+                for (int o = tid * 128; o < nstaged * 8; o += TW * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(nxy + o));
+                for (int o = tid * 128; o < nstaged * 16; o += TW * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(nrgbw + o));
+            }
+#endif
+            // ---------------- gather: this thread's column against the row ----------------
+            if (col_ok) {
+                const unsigned m_up = mask_mode ? ~mk[0] & sppmask : 0u, m_down = mask_mode ? ~mk[1] & sppmask : 0u;
+                const unsigned m_lall = ~mk[2] & sppmask, m_lnone = mask_mode ? ~mk[3] & sppmask : 0u;
+                const unsigned m_rall = ~mk[4] & sppmask, m_rnone = mask_mode ? ~mk[5] & sppmask : 0u;
+                // EDGE = -1: the visit of nominal pixel x - H, whose samples reach x only when they reach their
+                // rightmost column; +1: pixel x + H, leftmost column; 0: interior
+                auto visit = [&](const int d, auto edge_tag) {
+                    constexpr int EDGE = decltype(edge_tag)::value;
+                    const int nx = x + d;
+                    if (nx < P.sb.x0 || nx >= P.sb.x1) return;
+                    const int pl = nx - (cx0 - H);
+                    const float4 *pa = s_rec + pl * pitch;
+                    const unsigned char *pf = s_flag + pl * pitch;
+                    const unsigned coloff = (unsigned)((H - d) * COLB);  // this column inside the sample's block
+                    unsigned run_up = m_up, run_down = m_down, skip = 0u;
+                    if (EDGE < 0) { run_up &= m_rall; run_down &= m_rall; skip = m_rnone; }
+                    if (EDGE > 0) { run_up &= m_lall; run_down &= m_lall; skip = m_lnone; }
+                    // live rows of one sample against this column: DOWN = false rows 0..LIVE-1, weights in order;
+                    // true rows 1..LIVE, the mirrored class's weights in reverse
+                    auto body = [&](const float4 a, auto down_tag) {
+                        constexpr bool DOWN = decltype(down_tag)::value;
+                        const unsigned waddr = __float_as_uint(a.w) + coloff;
+                        float w[LIVE];
+#pragma unroll
+                        for (int k4 = 0; k4 < LIVE / 4; ++k4)
+                            lds_blob4(waddr + 16 * k4, w[4 * k4], w[4 * k4 + 1], w[4 * k4 + 2], w[4 * k4 + 3]);
+#pragma unroll
+                        for (int i = 0; i < LIVE; ++i) {
+                            if (DOWN) tap(i + 1, a.x, a.y, a.z, w[LIVE - 1 - i]);
+                            else tap(i, a.x, a.y, a.z, w[i]);
+                        }
+                    };
+                    // a sample of any kind, decided per lane
+                    auto general = [&](const int s) {
+                        const float4 a = pa[s];
+                        const unsigned fl = pf[s] & 15u;
+                        if (fl == CF_SLOW) {
+                            // no class: evaluate the CPU path's expressions for this (sample, column)
+                            const float2 p = __ldg(&gxy[(nx - sx0) * spp + s]);
+                            const float pdx = p.x - 0.5f, pdy = p.y - 0.5f;
+                            if (!(fabsf(pdx - (float)nx) <= 0.5f && fabsf(pdy - fny) <= 0.5f)) errbits |= ERRBIT_NOT_PIXEL_MAJOR;
+                            if (!(fx >= pdx - P.rx && fx <= pdx + P.rx)) return;
+                            const int ix = class_table_index((fx - pdx) * c16);
+#pragma unroll
+                            for (int j = 0; j < ROWS; ++j) {
+                                const float fy = fny + (float)(j - H);
+                                const bool reach = fy >= pdy - P.ry && fy <= pdy + P.ry;
+                                const int iy = class_table_index((fy - pdy) * c16);
+                                if (reach) tap(j, a.x, a.y, a.z, __ldg(&P.table[iy * 16 + ix]));
+                            }
+                            return;
+                        }
+                        if (EDGE < 0 && !(fl & CF_RIGHT)) return;
+                        if (EDGE > 0 && !(fl & CF_LEFT)) return;
+                        if (fl & CF_DOWN) {
+                            body(a, std::true_type{});
+                        } else {
+                            body(a, std::false_type{});
+                            if (fl & CF_BOTH) {  // phase 0: the last window row as well
+                                const unsigned cbase = sbase + CT_Q_OFFSET + K * CP.rowp;
+                                const unsigned cx = (__float_as_uint(a.w) - cbase) / (unsigned)BLK;
+                                tap(ROWS - 1, a.x, a.y, a.z, lds_blob1(sbase + CP.eoff + (cx * ROWS + (unsigned)(H - d)) * 4u));
+                            }
+                        }
+                    };
+                    int s = 0;
+                    while (s < spp) {
+                        const unsigned up = run_up >> s;
+                        if (up & 1u) {
+                            const int n = (int)min((unsigned)(__ffs((int)~up) - 1), (unsigned)(spp - s));
+#pragma unroll kClassUnroll
+                            for (int i = 0; i < n; ++i) body(pa[s + i], std::false_type{});
+                            s += n;
+                            continue;
+                        }
+                        const unsigned down = run_down >> s;
+                        if (down & 1u) {
+                            const int n = (int)min((unsigned)(__ffs((int)~down) - 1), (unsigned)(spp - s));
+#pragma unroll kClassUnroll
+                            for (int i = 0; i < n; ++i) body(pa[s + i], std::true_type{});
+                            s += n;
+                            continue;
+                        }
+                        const unsigned sk = skip >> s;
+                        if (sk & 1u) {
+                            s += (int)min((unsigned)(__ffs((int)~sk) - 1), (unsigned)(spp - s));
+                            continue;
+                        }
+                        general(s);
+                        ++s;
+                    }
+                };
+                // columns are visited left to right: the accumulation order of the CPU path
+                visit(-H, std::integral_constant<int, -1>{});
+#pragma unroll 1
+                for (int d = -H + 1; d <= H - 1; ++d) visit(d, std::integral_constant<int, 0>{});
+                visit(H, std::integral_constant<int, 1>{});
+            }
+            parity ^= 1;
+        }
+        // output row ny - H is complete: no later sample row reaches it
+        const int yo = ny - H;
+        if (col_ok && yo >= cy0 && yo < cy1) {
+            float r, g, b, w;
+            acc.get(0, r, g, b, w);
+            // non-finite radiance (a contract violation) shows in the sums: 0 * x is NaN for x = inf or NaN
+            const float z = r * 0.f + g * 0.f + b * 0.f + w * 0.f;
+            if (z != z) errbits |= ERRBIT_NONFINITE;
+            const size_t fo = (size_t)(yo - P.owned.y0) * (P.owned.x1 - P.owned.x0) + (x - P.owned.x0);
+            float4 px = P.film[fo];
+            float X, Y, Z;
+            rgb_to_xyz(r, g, b, X, Y, Z);
+            px.x += X; px.y += Y; px.z += Z; px.w += w;
+            P.film[fo] = px;
+        }
+#pragma unroll
+        for (int j = 0; j + 1 < ROWS; ++j) acc.move(j, j + 1);
+        acc.clear(ROWS - 1);
+    }
+    if (!(vmax <= 0.5f)) errbits |= ERRBIT_NOT_PIXEL_MAJOR;
+    if (errbits) atomicOr(P.err, (int)errbits);
+}
+
+// ---- launch ------------------------------------------------------------------------------------------------------
+
+static int class_env_int(const char *name, int dflt) {
+    const char *v = getenv(name);
+    return v && *v ? atoi(v) : dflt;
+}
+
+template <int H, int TW, bool FMA>
+static int launch_class(const ClassParams &CP0) {
+    ClassParams CP = CP0;
+    SplatParams &P = CP.S;
+    const size_t smem = ClassSmem<H, TW>::bytes(CP.blob_bytes, P.spp) + (size_t)class_env_int("PBRT_B200_SMEM_PAD", 0);
+    if (smem > 227 * 1024) return -1;
+    static int attr_device = -1;
+    if (attr_device != ctx().device) {
+        PB_CUDA(cudaFuncSetAttribute(splat_class_kernel<H, TW, FMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_device = ctx().device;
+    }
+    int per_sm = 0;
+    PB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, splat_class_kernel<H, TW, FMA>, TW, smem));
+    if (per_sm < 1) return -1;
+    const int cols = (bw(P.tb) + TW - 1) / TW;
+    const int rows = bh(P.tb);
+    // one wave: at most as many CTAs as are resident at once, strips no shorter than 4h rows
+    const int resident = ctx().sm_count * per_sm;
+    int segs = std::max(1, resident / cols);
+    segs = std::min(segs, std::max(1, rows / (4 * H)));
+    const int rpc = class_env_int("PBRT_B200_ROWS_PER_CTA", 0);
+    P.rows_per_cta = rpc > 0 ? rpc : (rows + segs - 1) / segs;
+    segs = (rows + P.rows_per_cta - 1) / P.rows_per_cta;
+    dim3 grid(cols, segs);
+    splat_class_kernel<H, TW, FMA><<<grid, TW, smem, ctx().stream>>>(CP);
+    PB_LAUNCH_CHECK("splat_class_kernel");
+    return PBRT_OK;
+}
+
+template <int H, bool FMA>
+static int class_pick_width(const ClassParams &CP) {
+    const int force = class_env_int("PBRT_B200_TW", 0);
+    if (force == 128) return launch_class<H, 128, FMA>(CP);
+    if (force == 64) return launch_class<H, 64, FMA>(CP);
+    if (force == 32) return launch_class<H, 32, FMA>(CP);
+    const int spp = CP.S.spp;
+    if (ClassSmem<H, 128>::bytes(CP.blob_bytes, spp) * 2 <= 226 * 1024) return launch_class<H, 128, FMA>(CP);
+    if (ClassSmem<H, 64>::bytes(CP.blob_bytes, spp) * 2 <= 226 * 1024) return launch_class<H, 64, FMA>(CP);
+    return launch_class<H, 32, FMA>(CP);
+}
+
+int launch_splat_class(PbrtFilm *f, const SplatParams &P, int mode) {
+    if (!f->class_bytes || P.tiles || class_env_int("PBRT_B200_NO_CLASS", 0)) return -1;
+    if (mode != PBRT_SPLAT_EXACT && mode != PBRT_SPLAT_FMA) return -1;
+    ClassGeom g;
+    if (!class_geom(P.rx, P.ry, &g) || g.H != f->class_h) return -1;
+    ClassParams CP;
+    CP.S = P;
+    CP.blob = reinterpret_cast<const uint4 *>(f->d_class);
+    CP.blob_bytes = f->class_bytes;
+    CP.rowp = g.ROWP;
+    CP.eoff = g.EOFF;
+    const bool fma = mode == PBRT_SPLAT_FMA;
+    if (g.H == 2) return fma ? class_pick_width<2, true>(CP) : class_pick_width<2, false>(CP);
+    return fma ? class_pick_width<4, true>(CP) : class_pick_width<4, false>(CP);
+}
+
+}  // namespace pb
+
+// [UTIL, test hook] the phase-class tables of a filter table, built on the host (no device needed): the blob the
+// kernel stages in shared memory and its geometry {H, K, NX, NXP, COLB, BLK, ROWP, EOFF, BYTES}.  Returns the blob's
+// size in bytes, 0 when the radius is not served by the class kernel; copies min(size, cap) bytes.
+extern "C" int pbrt_b200_debug_class_tables(const float table[256], float rx, float ry, uint8_t *out, int cap,
+                                            int32_t geom[9]) {
+    std::vector<unsigned char> blob;
+    pb::ClassGeom g;
+    if (!table || !pb::class_tables_host(table, rx, ry, &blob, &g)) return 0;
+    if (geom) {
+        const int v[9] = {g.H, g.K, g.NX, g.NXP, g.COLB, g.BLK, g.ROWP, g.EOFF, g.BYTES};
+        for (int i = 0; i < 9; ++i) geom[i] = v[i];
+    }
+    if (out && cap > 0) memcpy(out, blob.data(), std::min<size_t>(blob.size(), (size_t)cap));
+    return (int)blob.size();
+}
