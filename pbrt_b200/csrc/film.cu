@@ -42,10 +42,26 @@ static std::mutex g_init_mu;
 // (film.rs:73) and FilmTile is Send, so worker threads may call merge_film_tile concurrently.  Handles carry
 // mutable host-side state (staging buffers, cached tile index) and all work goes to one stream anyway.
 static std::recursive_mutex g_api_mu;
-#define PB_API_LOCK std::lock_guard<std::recursive_mutex> pb_api_lock_(pb::g_api_mu)
+// The CUDA current device is a per-host-thread setting: a worker thread that never called pbrt_b200_init would launch on
+// device 0 against streams and buffers of the bound device.  Every locked entry point therefore re-binds its thread.
+static void bind_thread() {
+    static thread_local int bound = -1;
+    if (ctx().ready && bound != ctx().device) {
+        cudaSetDevice(ctx().device);
+        bound = ctx().device;
+    }
+}
+struct ApiGuard {
+    std::lock_guard<std::recursive_mutex> lock;
+    ApiGuard() : lock(g_api_mu) { bind_thread(); }
+};
+#define PB_API_LOCK pb::ApiGuard pb_api_lock_
 
 int ensure_ready() {
-    if (ctx().ready) return PBRT_OK;
+    if (ctx().ready) {
+        bind_thread();
+        return PBRT_OK;
+    }
     return pbrt_b200_init(0);
 }
 
@@ -109,15 +125,16 @@ extern "C" int pbrt_b200_init(int device) {
     PB_CUDA(cudaSetDevice(device));
     cudaDeviceProp p;
     PB_CUDA(cudaGetDeviceProperties(&p, device));
-    if (p.major != 10)
+    if (p.major != 10 || p.minor != 0)
         return fail(PBRT_E_CUDA, "device %d is sm_%d%d; this library carries sm_100a code only", device, p.major,
                     p.minor);
     pb::Ctx &c = ctx();
     if (c.ready && c.device == device) return PBRT_OK;
-    if (!c.own_stream || c.device != device) {
-        PB_CUDA(cudaStreamCreateWithFlags(&c.own_stream, cudaStreamNonBlocking));
-        PB_CUDA(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
-    }
+    // one device per process (one process per GPU): streams, films and per-kernel attributes belong to it
+    if (c.ready)
+        return fail(PBRT_E_INVALID, "already bound to device %d; libpbrt_b200 serves one device per process", c.device);
+    PB_CUDA(cudaStreamCreateWithFlags(&c.own_stream, cudaStreamNonBlocking));
+    PB_CUDA(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
     c.stream = c.own_stream;
     c.device = device;
     c.sm_count = p.multiProcessorCount;
@@ -907,10 +924,12 @@ static int resolve_impl(const PbrtFilm *f, float splat_scale, void *out, int dst
         }
     }
     static int ppt_env = getenv("PBRT_B200_RES_PPT") ? atoi(getenv("PBRT_B200_RES_PPT")) : 0;
+    if (ppt_env != 0 && ppt_env != 1 && ppt_env != 2 && ppt_env != 4)
+        return fail(PBRT_E_INVALID, "PBRT_B200_RES_PPT=%d: pixels per thread must be 1, 2 or 4", ppt_env);
     const int PPT = ppt_env ? ppt_env : (BYTES ? 4 : 2);
     int blocks = (int)((f->npix + RES_THREADS * PPT - 1) / (RES_THREADS * PPT));
 #define RES_LAUNCH(N) resolve_kernel<BYTES, N><<<blocks, RES_THREADS, 0, ctx().stream>>>(f->d_xyzw, f->d_splat, (long long)f->npix, splat_scale, f->scale, d_out)
-    if (PPT == 1) RES_LAUNCH(1); else if (PPT == 2) RES_LAUNCH(2); else if (PPT == 8) RES_LAUNCH(8); else RES_LAUNCH(4);
+    if (PPT == 1) RES_LAUNCH(1); else if (PPT == 2) RES_LAUNCH(2); else RES_LAUNCH(4);
     PB_LAUNCH_CHECK("resolve_kernel");
     if (to_host) {
         PB_CUDA(cudaMemcpyAsync(out, d_out, bytes, cudaMemcpyDeviceToHost, ctx().stream));
@@ -1272,16 +1291,17 @@ static int add_samples_tile_impl(PbrtFilm *f, const int32_t sbv[4], int32_t spp,
     const void *dev[4] = {xy, rgbw, rgb3, sw};
     int set = 0;
     const bool async = src_is_device == PBRT_MEM_PINNED_ASYNC;
+    if ((async || split) && !f->pipe_ready) {
+        // the staging sets are about to be used for the first time: their events must exist before any kernel reads them
+        for (int i = 0; i < 2; ++i) {
+            PB_CUDA(cudaEventCreateWithFlags(&f->ev_staged[i], cudaEventDisableTiming));
+            PB_CUDA(cudaEventCreateWithFlags(&f->ev_consumed[i], cudaEventDisableTiming));
+        }
+        f->pipe_ready = true;
+    }
     if (async) {
         // upload on the copy stream into the staging set the previous-but-one call used; the kernel waits for
         // the upload, the next upload into this set waits for the kernel
-        if (!f->pipe_ready) {
-            for (int i = 0; i < 2; ++i) {
-                PB_CUDA(cudaEventCreateWithFlags(&f->ev_staged[i], cudaEventDisableTiming));
-                PB_CUDA(cudaEventCreateWithFlags(&f->ev_consumed[i], cudaEventDisableTiming));
-            }
-            f->pipe_ready = true;
-        }
         set = f->pipe_turn;
         f->pipe_turn ^= 1;
         for (int k = 0; k < 4; ++k)
@@ -1330,7 +1350,7 @@ static int add_samples_tile_impl(PbrtFilm *f, const int32_t sbv[4], int32_t spp,
     }
     int rc = pb::launch_splat_tile(f, sb, tb, spp, (const float2 *)dev[0], (const float4 *)dev[1], mode);
     // also after a synchronous call that borrowed set 0's interleave buffer: the next upload into it must wait
-    if (async || (split && f->pipe_ready)) PB_CUDA(cudaEventRecord(f->ev_consumed[set], ctx().stream));
+    if (async || split) PB_CUDA(cudaEventRecord(f->ev_consumed[set], ctx().stream));
     return rc;
 }
 

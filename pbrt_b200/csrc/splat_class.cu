@@ -253,10 +253,9 @@ __device__ __forceinline__ u64 cpack2(float lo, float hi) {
 __device__ __forceinline__ void cunpack2(u64 v, float &lo, float &hi) {
     asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
 }
-__device__ __forceinline__ u64 cadd2(u64 a, u64 b) {
-    u64 r;
-    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-    return r;
+// in place: the accumulator keeps its register pair across the unrolled loop (no copies at the back edge)
+__device__ __forceinline__ void cadd2(u64 &a, u64 b) {
+    asm("add.rn.f32x2 %0, %0, %1;" : "+l"(a) : "l"(b));
 }
 // Loads from the table blob, which is constant once the barrier after its fill has passed.  Not volatile: the address
 // depends on data read after that barrier, so the compiler may schedule these freely across the unrolled samples.
@@ -285,7 +284,7 @@ __device__ __forceinline__ int class_table_index(float v) {
 // (b*w, w) addend pair costs a MOV per tap since w arrives in a register of its own; 1: (r,g) packed, b and w scalar;
 // 2: four scalars.  The fused variant (PBRT_SPLAT_FMA) always uses 2.  Indices are compile-time after unrolling.
 #ifndef PBRT_CLASS_ACC
-#define PBRT_CLASS_ACC 1
+#define PBRT_CLASS_ACC 0
 #endif
 template <int ROWS, int LAYOUT>
 struct ClassAcc {
@@ -308,9 +307,9 @@ struct ClassAcc {
     // exact: products by scalar multiplies (rounded like the CPU's), then added — ptxas would fuse a packed multiply
     // feeding a packed add into one FFMA2 even under --fmad=false
     __device__ __forceinline__ void tap(const int j, const float cr, const float cg, const float cb, const float wt) {
-        if (LAYOUT <= 1) rg[j] = cadd2(rg[j], cpack2(cr * wt, cg * wt));
+        if (LAYOUT <= 1) cadd2(rg[j], cpack2(cr * wt, cg * wt));
         else { r[j] += cr * wt; g[j] += cg * wt; }
-        if (LAYOUT == 0) bw[j] = cadd2(bw[j], cpack2(cb * wt, wt));
+        if (LAYOUT == 0) cadd2(bw[j], cpack2(cb * wt, wt));
         else { b[j] += cb * wt; w[j] += wt; }
     }
     // same order, one rounding per accumulate (LAYOUT 2 only)
@@ -331,15 +330,18 @@ struct ClassSmem {
 };
 
 #ifndef PBRT_CLASS_PREPASS_BATCH
-#define PBRT_CLASS_PREPASS_BATCH 6
+#define PBRT_CLASS_PREPASS_BATCH 4
 #endif
 #ifndef PBRT_CLASS_UNROLL
 #define PBRT_CLASS_UNROLL 4
 #endif
 constexpr int kClassUnroll = PBRT_CLASS_UNROLL;  // samples per trip of a run's loop
 
+#ifndef PBRT_CLASS_RESIDENT_THREADS
+#define PBRT_CLASS_RESIDENT_THREADS 512  // 4 CTAs of 128 threads per SM: 128 registers per thread
+#endif
 template <int H, int TW, bool FMA>
-__global__ void __launch_bounds__(TW, 512 / TW) splat_class_kernel(ClassParams CP) {
+__global__ void __launch_bounds__(TW, PBRT_CLASS_RESIDENT_THREADS / TW) splat_class_kernel(ClassParams CP) {
     typedef ClassCfg<H> C;
     constexpr int ROWS = C::ROWS, LIVE = C::LIVE, K = C::K, COLB = C::COLB, BLK = C::BLK;
     constexpr int NPX = ClassSmem<H, TW>::NPX;
@@ -413,20 +415,31 @@ __global__ void __launch_bounds__(TW, 512 / TW) splat_class_kernel(ClassParams C
             float fnx = (float)(sx0 + q0);
             unsigned andf = 15u, orf = 0u;
             constexpr int U = PBRT_CLASS_PREPASS_BATCH;
-            for (int e0 = tid; e0 < nstaged; e0 += U * TW) {
+            const float2 *lxy = gxy + tid;  // this thread's next sample; the batch is lxy[0], lxy[TW], ...
+            const float4 *lrgbw = grgbw + tid;
+            for (int e0 = tid; e0 < nstaged; e0 += U * TW, lxy += U * TW, lrgbw += U * TW) {
                 float2 p[U];
                 float4 L[U];
+                const bool full = e0 + (U - 1) * TW < nstaged;
+                if (full) {
 #pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    if (e0 + u * TW < nstaged) {
-                        p[u] = ldg_stream(&gxy[e0 + u * TW]);
-                        L[u] = ldg_stream(&grgbw[e0 + u * TW]);
+                    for (int u = 0; u < U; ++u) {
+                        p[u] = ldg_stream(lxy + u * TW);
+                        L[u] = ldg_stream(lrgbw + u * TW);
+                    }
+                } else {
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        if (e0 + u * TW < nstaged) {
+                            p[u] = ldg_stream(lxy + u * TW);
+                            L[u] = ldg_stream(lrgbw + u * TW);
+                        }
                     }
                 }
                 if (clamp_on) {  // max_sample_luminance, off (infinite) in every BASELINE config: kept out of the main body
 #pragma unroll
                     for (int u = 0; u < U; ++u) {
-                        if (e0 + u * TW < nstaged) {
+                        if (full || e0 + u * TW < nstaged) {
                             const float ly = luminance(L[u].x, L[u].y, L[u].z);
                             if (ly > P.max_lum) {
                                 const float sc = P.max_lum / ly;
@@ -435,70 +448,76 @@ __global__ void __launch_bounds__(TW, 512 / TW) splat_class_kernel(ClassParams C
                         }
                     }
                 }
-                auto process = [&](auto wrap_tag) {
-                    constexpr bool WRAP = decltype(wrap_tag)::value;
+                // One sample: phase, class, record.  CAREFUL = the pixels next to the origin, whose phase can be finer
+                // than 2^-22 (bounds found on the host decide); otherwise the classes are the ideal ones.
+                auto one = [&](const int u, auto careful_tag) {
+                    constexpr bool CAREFUL = decltype(careful_tag)::value;
+                    const float cr = L[u].x * L[u].w, cg = L[u].y * L[u].w, cb = L[u].z * L[u].w;
+                    const float pdx = p[u].x - 0.5f, pdy = p[u].y - 0.5f;
+                    // phase: exact (Sterbenz) for a sample inside its nominal pixel
+                    const float wx = pdx - fnx, wy = pdy - fny;
+                    // contract: the sample lies in its nominal pixel (a NaN phase reaches the slow path instead)
+                    vmax = fmaxf(vmax, fmaxf(fabsf(wx), fabsf(wy)));
+                    unsigned offx, offy;
+                    if (!CAREFUL) {
+                        auto classify = [&](const float w, const unsigned lut) {
+                            float t = __fmaf_rn(w, (float)K, 0.5f * (float)K);
+                            t = fminf(fabsf(t), (float)(CT_LUT_ENTRIES - 1));
+                            const unsigned cell = (unsigned)__float_as_int(__fadd_rd(t, 8388608.f));
+                            float point, oi, op, pad;
+                            lds_blob4(__dp4a(cell, 16u, lut), point, oi, op, pad);
+                            return __float_as_uint(w == point ? op : oi);
+                        };
+                        offx = classify(wx, sbase + CT_LUT_X);
+                        offy = classify(wy, sbase + CT_LUT_Y);
+                    } else {
+                        auto classify = [&](const float w, const unsigned lut, const unsigned slow) {
+                            float t = __fmaf_rn(w, (float)K, 0.5f * (float)K + 0.5f);
+                            t = fminf(fabsf(t), (float)(CT_CARE_ENTRIES - 1));
+                            const unsigned cell = (unsigned)__float_as_int(__fadd_rd(t, 8388608.f));
+                            const unsigned e = __dp4a(cell, 32u, lut);
+                            float glo, ghi, point, pad0, ob, op, oa, pad1;
+                            lds_blob4(e, glo, ghi, point, pad0);
+                            lds_blob4(e + 16, ob, op, oa, pad1);
+                            return w < glo ? __float_as_uint(ob)
+                                           : (w > ghi ? __float_as_uint(oa) : (w == point ? __float_as_uint(op) : slow));
+                        };
+                        offx = classify(wx, sbase + CT_CARE_X, CT_SLOW_X);
+                        offy = classify(wy, sbase + CT_CARE_Y, CT_SLOW_Y);
+                    }
+                    // The classes take "pixel n + H is reached" to mean w >= 0.  The CPU path asks whether
+                    // n + H <= floor(pd + r) in floats, and pd + r can round up to the integer when it crosses a
+                    // power of two: such a sample is none of the classes.  (ceil(pd - r) has no such case: the
+                    // difference is exact wherever the result is a pixel coordinate >= 0.)
+                    const unsigned sum = offx + offy;
+                    const bool ok = sum < CT_SLOW_X && !(wx < 0.f && fnx + rH <= pdx + rH) && !(wy < 0.f && fnyH <= pdy + rH);
+                    const unsigned fl = ok ? (sum & 15u) : CF_SLOW;
+                    sts_rec(a_rec + 16u * (unsigned)slot, cr, cg, cb, sum & ~15u);
+                    sts_flag(a_flag + (unsigned)slot, fl);
+                    andf &= fl;
+                    orf |= fl;
+                };
+                // pixels this batch touches: fnx .. fnx + (U - 1) * (dq + 1) at most
+                const bool careful = hazard_y || (fnx < 2.5f && fnx + (float)((U - 1) * (dq + 1)) > -2.5f);
+                if (full && dr == 0 && !careful) {
 #pragma unroll
                     for (int u = 0; u < U; ++u) {
-                        if (e0 + u * TW < nstaged) {
-                            const float cr = L[u].x * L[u].w, cg = L[u].y * L[u].w, cb = L[u].z * L[u].w;
-                            const float pdx = p[u].x - 0.5f, pdy = p[u].y - 0.5f;
-                            // phase: exact (Sterbenz) for a sample inside its nominal pixel
-                            const float wx = pdx - fnx, wy = pdy - fny;
-                            // contract: the sample lies in its nominal pixel (a NaN phase reaches the slow path instead)
-                            vmax = fmaxf(vmax, fmaxf(fabsf(wx), fabsf(wy)));
-                            unsigned offx, offy;
-                            if (!(hazard_y || fabsf(fnx) < 2.5f)) {
-                                // |pd| >= 2: the phase is a multiple of 2^-22, the classes are the ideal ones
-                                auto classify = [&](const float w, const unsigned lut) {
-                                    float t = __fmaf_rn(w, (float)K, 0.5f * (float)K);
-                                    t = fminf(fabsf(t), (float)(CT_LUT_ENTRIES - 1));
-                                    const unsigned cell = (unsigned)__float_as_int(__fadd_rd(t, 8388608.f));
-                                    float point, oi, op, pad;
-                                    lds_blob4(__dp4a(cell, 16u, lut), point, oi, op, pad);
-                                    return __float_as_uint(w == point ? op : oi);
-                                };
-                                offx = classify(wx, sbase + CT_LUT_X);
-                                offy = classify(wy, sbase + CT_LUT_Y);
-                            } else {
-                                // next to the origin the phase can be finer than 2^-22: bounds found on the host decide
-                                auto classify = [&](const float w, const unsigned lut, const unsigned slow) {
-                                    float t = __fmaf_rn(w, (float)K, 0.5f * (float)K + 0.5f);
-                                    t = fminf(fabsf(t), (float)(CT_CARE_ENTRIES - 1));
-                                    const unsigned cell = (unsigned)__float_as_int(__fadd_rd(t, 8388608.f));
-                                    const unsigned e = __dp4a(cell, 32u, lut);
-                                    float glo, ghi, point, pad0, ob, op, oa, pad1;
-                                    lds_blob4(e, glo, ghi, point, pad0);
-                                    lds_blob4(e + 16, ob, op, oa, pad1);
-                                    return w < glo ? __float_as_uint(ob)
-                                                   : (w > ghi ? __float_as_uint(oa) : (w == point ? __float_as_uint(op) : slow));
-                                };
-                                offx = classify(wx, sbase + CT_CARE_X, CT_SLOW_X);
-                                offy = classify(wy, sbase + CT_CARE_Y, CT_SLOW_Y);
-                            }
-                            // The classes take "pixel n + H is reached" to mean w >= 0.  The CPU path asks whether
-                            // n + H <= floor(pd + r) in floats, and pd + r can round up to the integer when it crosses a
-                            // power of two: such a sample is none of the classes.  (ceil(pd - r) has no such case: the
-                            // difference is exact wherever the result is a pixel coordinate >= 0.)
-                            const bool ok = offx + offy < CT_SLOW_X && !(wx < 0.f && fnx + rH <= pdx + rH) &&
-                                            !(wy < 0.f && fnyH <= pdy + rH);
-                            const unsigned sum = offx + offy;
-                            const unsigned fl = ok ? (sum & 15u) : CF_SLOW;
-                            const unsigned meta = (sbase + sum) & ~15u;
-                            sts_rec(a_rec + 16u * (unsigned)slot, cr, cg, cb, meta);
-                            sts_flag(a_flag + (unsigned)slot, fl);
-                            andf &= fl;
-                            orf |= fl;
-                        }
+                        one(u, std::false_type{});
                         slot += slot_step;
                         fnx += fdq;
-                        if (WRAP) {
-                            sidx += dr;
-                            if (sidx >= spp) { sidx -= spp; slot += pitch - spp; fnx += 1.f; }
-                        }
                     }
-                };
-                if (dr == 0) process(std::false_type{});
-                else process(std::true_type{});
+                } else {
+                    // tail of the row, pixels next to the origin, or spp not dividing the strip width: bounds-checked,
+                    // with the careful classification (valid for every phase, a dozen instructions longer)
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        if (e0 + u * TW < nstaged) one(u, std::true_type{});
+                        slot += slot_step;
+                        fnx += fdq;
+                        sidx += dr;
+                        if (sidx >= spp) { sidx -= spp; slot += pitch - spp; fnx += 1.f; }
+                    }
+                }
             }
             // per sample index: is every sample of the strip "up" / "down", does every / no sample reach the outermost
             // column on the left / right.  Words: 0 !up 1 !down 2 !left-all 3 !left-none 4 !right-all 5 !right-none
@@ -528,41 +547,92 @@ __global__ void __launch_bounds__(TW, 512 / TW) splat_class_kernel(ClassParams C
                 const unsigned m_up = mask_mode ? ~mk[0] & sppmask : 0u, m_down = mask_mode ? ~mk[1] & sppmask : 0u;
                 const unsigned m_lall = ~mk[2] & sppmask, m_lnone = mask_mode ? ~mk[3] & sppmask : 0u;
                 const unsigned m_rall = ~mk[4] & sppmask, m_rnone = mask_mode ? ~mk[5] & sppmask : 0u;
-                // EDGE = -1: the visit of nominal pixel x - H, whose samples reach x only when they reach their
-                // rightmost column; +1: pixel x + H, leftmost column; 0: interior
-                auto visit = [&](const int d, auto edge_tag) {
-                    constexpr int EDGE = decltype(edge_tag)::value;
+                // A "simple" row (every stratified row without a phase-0 or classless sample): sample indices 0..n_up-1 are
+                // "up" everywhere in the strip, the rest "down", and each index either always or never reaches an
+                // outermost column.  Its visits are two loops with no per-sample decisions.
+                const int n_up = __popc(m_up);
+                const bool simple_rows = mask_mode && m_up == ((1u << n_up) - 1u) && (m_up | m_down) == sppmask;
+                const bool simple_left = (m_lall | m_lnone) == sppmask, simple_right = (m_rall | m_rnone) == sppmask;
+                // Halo rows (sample rows above / below the output rows of this CTA) reach only a few owned rows: window
+                // rows j >= H + t for the t-th row above, j <= H - b for the b-th row below.  Computing more is harmless
+                // (rows that are not owned are never flushed), so this only selects cheaper bodies.
+                const int band = ny < cy0 ? cy0 - ny : (ny >= cy1 ? -(ny - cy1 + 1) : 0);
+                // Columns are visited left to right: the accumulation order of the CPU path.  The visit of nominal pixel
+                // x - H (d = -H) sees only samples that reach their rightmost column, x + H only their leftmost.
+#pragma unroll 1
+                for (int d = -H; d <= H; ++d) {
                     const int nx = x + d;
-                    if (nx < P.sb.x0 || nx >= P.sb.x1) return;
+                    if (nx < P.sb.x0 || nx >= P.sb.x1) continue;
                     const int pl = nx - (cx0 - H);
                     const float4 *pa = s_rec + pl * pitch;
                     const unsigned char *pf = s_flag + pl * pitch;
-                    const unsigned coloff = (unsigned)((H - d) * COLB);  // this column inside the sample's block
-                    unsigned run_up = m_up, run_down = m_down, skip = 0u;
-                    if (EDGE < 0) { run_up &= m_rall; run_down &= m_rall; skip = m_rnone; }
-                    if (EDGE > 0) { run_up &= m_lall; run_down &= m_lall; skip = m_lnone; }
-                    // live rows of one sample against this column: DOWN = false rows 0..LIVE-1, weights in order;
-                    // true rows 1..LIVE, the mirrored class's weights in reverse
-                    auto body = [&](const float4 a, auto down_tag) {
+                    // shared-window address of this column inside the block at offset 0
+                    const unsigned qcol = sbase + (unsigned)((H - d) * COLB);
+                    const bool interior = d != -H && d != H;
+                    unsigned run_up = m_up, run_down = m_down, live = sppmask;
+                    if (d == -H) { run_up &= m_rall; run_down &= m_rall; live &= ~m_rnone; }
+                    if (d == H) { run_up &= m_lall; run_down &= m_lall; live &= ~m_lnone; }
+                    // taps I0..I1-1 of one sample against this column: DOWN = false: tap i is window row i, weights in
+                    // order; true: window row i + 1, the mirrored class's weights in reverse
+                    auto body = [&](const float4 a, auto down_tag, auto i0_tag, auto i1_tag) {
                         constexpr bool DOWN = decltype(down_tag)::value;
-                        const unsigned waddr = __float_as_uint(a.w) + coloff;
+                        constexpr int I0 = decltype(i0_tag)::value, I1 = decltype(i1_tag)::value;
+                        const unsigned waddr = qcol + __float_as_uint(a.w);
                         float w[LIVE];
 #pragma unroll
                         for (int k4 = 0; k4 < LIVE / 4; ++k4)
                             lds_blob4(waddr + 16 * k4, w[4 * k4], w[4 * k4 + 1], w[4 * k4 + 2], w[4 * k4 + 3]);
 #pragma unroll
-                        for (int i = 0; i < LIVE; ++i) {
+                        for (int i = I0; i < I1; ++i) {
                             if (DOWN) tap(i + 1, a.x, a.y, a.z, w[LIVE - 1 - i]);
                             else tap(i, a.x, a.y, a.z, w[i]);
                         }
                     };
+                    typedef std::integral_constant<int, 0> I_0;
+                    typedef std::integral_constant<int, LIVE> I_LIVE;
+                    // n consecutive samples / the samples whose bits are set, all of one kind
+                    auto run = [&](const float4 *q, const int n, auto down_tag, auto i0_tag, auto i1_tag) {
+                        if (decltype(i0_tag)::value >= decltype(i1_tag)::value) return;
+#pragma unroll kClassUnroll
+                        for (int i = 0; i < n; ++i) body(q[i], down_tag, i0_tag, i1_tag);
+                    };
+                    auto run_bits = [&](unsigned bits, auto down_tag, auto i0_tag, auto i1_tag) {
+                        if (decltype(i0_tag)::value >= decltype(i1_tag)::value) return;
+                        while (bits) {
+                            const int s0 = __ffs((int)bits) - 1;
+                            bits &= bits - 1;
+                            body(pa[s0], down_tag, i0_tag, i1_tag);
+                        }
+                    };
+                    if (simple_rows && (interior || (d == -H ? simple_right : simple_left))) {
+                        // up-run with taps [U0, U1), then down-run with taps [D0, D1)
+                        auto visit = [&](auto u0, auto u1, auto d0, auto d1) {
+                            if (interior) {
+                                run(pa, n_up, std::false_type{}, u0, u1);
+                                run(pa + n_up, spp - n_up, std::true_type{}, d0, d1);
+                            } else {
+                                run_bits(run_up, std::false_type{}, u0, u1);
+                                run_bits(run_down, std::true_type{}, d0, d1);
+                            }
+                        };
+                        typedef std::integral_constant<int, 1> I_1;
+                        typedef std::integral_constant<int, LIVE - 1> I_L1;
+                        typedef std::integral_constant<int, LIVE - 2> I_L2;
+                        typedef std::integral_constant<int, 2> I_2;
+                        if (H != 2 || band == 0 || band > 2 || band < -2) visit(I_0{}, I_LIVE{}, I_0{}, I_LIVE{});
+                        else if (band == 2) visit(I_0{}, I_0{}, I_L1{}, I_LIVE{});      // window row 4: the last tap of "down"
+                        else if (band == 1) visit(I_L1{}, I_LIVE{}, I_L2{}, I_LIVE{});  // rows 3, 4
+                        else if (band == -1) visit(I_0{}, I_2{}, I_0{}, I_1{});         // rows 0, 1
+                        else visit(I_0{}, I_1{}, I_0{}, I_0{});                         // row 0: the first tap of "up"
+                        continue;
+                    }
                     // a sample of any kind, decided per lane
-                    auto general = [&](const int s) {
+                    auto general = [&](const int s, const int c0) {
                         const float4 a = pa[s];
                         const unsigned fl = pf[s] & 15u;
                         if (fl == CF_SLOW) {
                             // no class: evaluate the CPU path's expressions for this (sample, column)
-                            const float2 p = __ldg(&gxy[(nx - sx0) * spp + s]);
+                            const float2 p = __ldg(&gxy[(nx - sx0) * spp + c0 + s]);
                             const float pdx = p.x - 0.5f, pdy = p.y - 0.5f;
                             if (!(fabsf(pdx - (float)nx) <= 0.5f && fabsf(pdy - fny) <= 0.5f)) errbits |= ERRBIT_NOT_PIXEL_MAJOR;
                             if (!(fx >= pdx - P.rx && fx <= pdx + P.rx)) return;
@@ -576,51 +646,49 @@ __global__ void __launch_bounds__(TW, 512 / TW) splat_class_kernel(ClassParams C
                             }
                             return;
                         }
-                        if (EDGE < 0 && !(fl & CF_RIGHT)) return;
-                        if (EDGE > 0 && !(fl & CF_LEFT)) return;
+                        if (d == -H && !(fl & CF_RIGHT)) return;
+                        if (d == H && !(fl & CF_LEFT)) return;
                         if (fl & CF_DOWN) {
-                            body(a, std::true_type{});
+                            body(a, std::true_type{}, I_0{}, I_LIVE{});
                         } else {
-                            body(a, std::false_type{});
+                            body(a, std::false_type{}, I_0{}, I_LIVE{});
                             if (fl & CF_BOTH) {  // phase 0: the last window row as well
-                                const unsigned cbase = sbase + CT_Q_OFFSET + K * CP.rowp;
-                                const unsigned cx = (__float_as_uint(a.w) - cbase) / (unsigned)BLK;
+                                const unsigned cx = (__float_as_uint(a.w) - (unsigned)(CT_Q_OFFSET + K * CP.rowp)) / (unsigned)BLK;
                                 tap(ROWS - 1, a.x, a.y, a.z, lds_blob1(sbase + CP.eoff + (cx * ROWS + (unsigned)(H - d)) * 4u));
                             }
                         }
                     };
-                    int s = 0;
-                    while (s < spp) {
-                        const unsigned up = run_up >> s;
-                        if (up & 1u) {
-                            const int n = (int)min((unsigned)(__ffs((int)~up) - 1), (unsigned)(spp - s));
-#pragma unroll kClassUnroll
-                            for (int i = 0; i < n; ++i) body(pa[s + i], std::false_type{});
-                            s += n;
-                            continue;
+                    // one segment: a run of consecutive indices (always, at an interior column) or scattered ones
+                    auto segment = [&](const unsigned seg, auto down_tag) {
+                        const int first = __ffs((int)seg) - 1;
+                        const unsigned shifted = seg >> first;
+                        if ((shifted & (shifted + 1u)) == 0u) run(pa + first, __popc(seg), down_tag, I_0{}, I_LIVE{});
+                        else run_bits(seg, down_tag, I_0{}, I_LIVE{});
+                    };
+                    // Any other row: the live samples in stream order, cut into segments of one kind.  Skipped samples do
+                    // not end a segment.  Sample indices go in chunks of 32 (the masks describe the first chunk; above 32
+                    // spp every sample is general).
+                    for (int c0 = 0; c0 < spp; c0 += 32, pa += 32, pf += 32) {
+                        unsigned rem = c0 == 0 ? live : (spp - c0 >= 32 ? 0xffffffffu : (1u << (spp - c0)) - 1u);
+                        while (rem) {
+                            const unsigned low = rem & (0u - rem);
+                            if (low & run_up) {
+                                const unsigned nb = rem & ~run_up;  // live samples that are not "up": the first one ends the segment
+                                const unsigned seg = nb ? rem & ((nb & (0u - nb)) - 1u) : rem;
+                                segment(seg, std::false_type{});
+                                rem &= ~seg;
+                            } else if (low & run_down) {
+                                const unsigned nb = rem & ~run_down;
+                                const unsigned seg = nb ? rem & ((nb & (0u - nb)) - 1u) : rem;
+                                segment(seg, std::true_type{});
+                                rem &= ~seg;
+                            } else {
+                                general(__ffs((int)low) - 1, c0);
+                                rem &= ~low;
+                            }
                         }
-                        const unsigned down = run_down >> s;
-                        if (down & 1u) {
-                            const int n = (int)min((unsigned)(__ffs((int)~down) - 1), (unsigned)(spp - s));
-#pragma unroll kClassUnroll
-                            for (int i = 0; i < n; ++i) body(pa[s + i], std::true_type{});
-                            s += n;
-                            continue;
-                        }
-                        const unsigned sk = skip >> s;
-                        if (sk & 1u) {
-                            s += (int)min((unsigned)(__ffs((int)~sk) - 1), (unsigned)(spp - s));
-                            continue;
-                        }
-                        general(s);
-                        ++s;
                     }
-                };
-                // columns are visited left to right: the accumulation order of the CPU path
-                visit(-H, std::integral_constant<int, -1>{});
-#pragma unroll 1
-                for (int d = -H + 1; d <= H - 1; ++d) visit(d, std::integral_constant<int, 0>{});
-                visit(H, std::integral_constant<int, 1>{});
+                }
             }
             parity ^= 1;
         }
@@ -687,6 +755,7 @@ template <int H, bool FMA>
 static int class_pick_width(const ClassParams &CP) {
     const int force = class_env_int("PBRT_B200_TW", 0);
     if (force == 128) return launch_class<H, 128, FMA>(CP);
+    if (force == 96) return launch_class<H, 96, FMA>(CP);
     if (force == 64) return launch_class<H, 64, FMA>(CP);
     if (force == 32) return launch_class<H, 32, FMA>(CP);
     const int spp = CP.S.spp;
