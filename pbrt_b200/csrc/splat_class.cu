@@ -319,6 +319,33 @@ struct ClassAcc {
     }
 };
 
+// Slow path: a sample no class describes.  Evaluates the CPU path's expressions for one (sample, output column) from
+// scratch — out of line and self-contained, so that nothing it needs stays live in the gather loops.  Returns the weight
+// of each window row (0 where the sample does not reach: adding (L * 0, 0) changes nothing) and reports a sample outside
+// its nominal pixel.
+template <int ROWS>
+struct SlowWeights { float w[ROWS]; int out_of_pixel; };
+
+template <int H>
+__device__ __noinline__ SlowWeights<2 * H + 1> class_slow_weights(const float2 *xy, const float *table, size_t index, int nx,
+                                                                  int ny, int x, float rx, float ry) {
+    SlowWeights<2 * H + 1> r;
+    const float2 p = __ldg(&xy[index]);
+    const float pdx = p.x - 0.5f, pdy = p.y - 0.5f, fx = (float)x, fny = (float)ny;
+    const float c16 = (1.f / (float)H) * 16.f;
+    r.out_of_pixel = !(fabsf(pdx - (float)nx) <= 0.5f && fabsf(pdy - fny) <= 0.5f);
+    const bool reach_x = fx >= pdx - rx && fx <= pdx + rx;
+    const int ix = class_table_index((fx - pdx) * c16);
+#pragma unroll
+    for (int j = 0; j < 2 * H + 1; ++j) {
+        const float fy = fny + (float)(j - H);
+        const bool reach = reach_x && fy >= pdy - ry && fy <= pdy + ry;
+        const int iy = class_table_index((fy - pdy) * c16);
+        r.w[j] = reach ? __ldg(&table[iy * 16 + ix]) : 0.f;
+    }
+    return r;
+}
+
 template <int H, int TW>
 struct ClassSmem {
     static constexpr int NPX = TW + 2 * H;
@@ -535,11 +562,13 @@ __global__ void __launch_bounds__(TW, PBRT_CLASS_RESIDENT_THREADS / TW) splat_cl
             if (tid < 8) s_mask[(parity ^ 1) * 8 + tid] = 0u;  // last read before this row's first barrier
             // pull the next sample row of this strip into L2 while this one is gathered
 #ifndef PBRT_NO_PREFETCH
-            if (ny + 1 < P.sb.y1 && ny + 1 < cy1 + H) {
-                const char *nxy = reinterpret_cast<const char *>(gxy + (size_t)W * spp);
-                const char *nrgbw = reinterpret_cast<const char *>(grgbw + (size_t)W * spp);
-                for (int o = tid * 128; o < nstaged * 8; o += TW * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(nxy + o));
-                for (int o = tid * 128; o < nstaged * 16; o += TW * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(nrgbw + o));
+            if (tid == 0 && ny + 1 < P.sb.y1 && ny + 1 < cy1 + H) {
+                // one bulk prefetch per stream, in whole 16-byte granules inside the run
+                const size_t bxy = reinterpret_cast<size_t>(gxy + (size_t)W * spp);
+                const size_t nxy = (bxy + 15) & ~(size_t)15;
+                const size_t nrgbw = reinterpret_cast<size_t>(grgbw + (size_t)W * spp);
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(nxy), "r"((unsigned)(bxy + (size_t)nstaged * 8 - nxy) & ~15u) : "memory");
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(nrgbw), "r"((unsigned)(nstaged * 16)) : "memory");
             }
 #endif
             // ---------------- gather: this thread's column against the row ----------------
@@ -631,19 +660,12 @@ __global__ void __launch_bounds__(TW, PBRT_CLASS_RESIDENT_THREADS / TW) splat_cl
                         const float4 a = pa[s];
                         const unsigned fl = pf[s] & 15u;
                         if (fl == CF_SLOW) {
-                            // no class: evaluate the CPU path's expressions for this (sample, column)
-                            const float2 p = __ldg(&gxy[(nx - sx0) * spp + c0 + s]);
-                            const float pdx = p.x - 0.5f, pdy = p.y - 0.5f;
-                            if (!(fabsf(pdx - (float)nx) <= 0.5f && fabsf(pdy - fny) <= 0.5f)) errbits |= ERRBIT_NOT_PIXEL_MAJOR;
-                            if (!(fx >= pdx - P.rx && fx <= pdx + P.rx)) return;
-                            const int ix = class_table_index((fx - pdx) * c16);
+                            // no class: the CPU path's expressions for this (sample, column)
+                            const size_t index = ((size_t)(ny - P.sb.y0) * (P.sb.x1 - P.sb.x0) + (nx - P.sb.x0)) * (size_t)spp + c0 + s;
+                            const SlowWeights<ROWS> sw = class_slow_weights<H>(P.xy, P.table, index, nx, ny, x, P.rx, P.ry);
+                            if (sw.out_of_pixel) errbits |= ERRBIT_NOT_PIXEL_MAJOR;
 #pragma unroll
-                            for (int j = 0; j < ROWS; ++j) {
-                                const float fy = fny + (float)(j - H);
-                                const bool reach = fy >= pdy - P.ry && fy <= pdy + P.ry;
-                                const int iy = class_table_index((fy - pdy) * c16);
-                                if (reach) tap(j, a.x, a.y, a.z, __ldg(&P.table[iy * 16 + ix]));
-                            }
+                            for (int j = 0; j < ROWS; ++j) tap(j, a.x, a.y, a.z, sw.w[j]);
                             return;
                         }
                         if (d == -H && !(fl & CF_RIGHT)) return;

@@ -142,6 +142,26 @@ def test_samples_on_exact_pixel_and_half_pixel_positions(gpu, orc):
         assert np.array_equal(u32(film.read_pixels()), u32(of.pixels())), name
 
 
+@pytest.mark.parametrize("name", ["gaussian", "lanczos"])
+def test_phases_one_ulp_below_a_pixel_centre_at_power_of_two_coordinates(gpu, orc, name):
+    """pd + r crosses into a coarser float grid just below a power of two: a sample one ulp left of (above) a pixel
+    centre then reaches the pixel r to its right (below) although its phase is negative.  Snap a third of the samples
+    there, on both axes, around x = 1024 and y = 32."""
+    def snap(xy, rgbw):
+        xy = xy.copy()
+        c = np.floor(xy) + np.float32(0.5)
+        below = np.nextafter(c, np.float32(-np.inf)).astype(np.float32)
+        above = np.nextafter(c, np.float32(np.inf)).astype(np.float32)
+        xy[0::6, 0] = below[0::6, 0]
+        xy[1::6, 1] = below[1::6, 1]
+        xy[2::6] = below[2::6]
+        xy[3::6, 0] = above[3::6, 0]
+        xy[4::6] = c[4::6]
+        return xy, rgbw
+    film, of = run_pair(gpu, orc, name, (1100, 48), [0, 0, 1, 1], (1008, 20, 1040, 44), 16, gpu.SPLAT_EXACT, jitter=snap)
+    assert np.array_equal(u32(film.read_pixels()), u32(of.pixels()))
+
+
 def test_max_sample_luminance_and_weights(gpu, orc):
     def bright(xy, rgbw):
         rgbw = rgbw.copy()
