@@ -147,6 +147,16 @@ int pbrt_film_geometry(int32_t xres, int32_t yres, const float crop_window[4], c
 int pbrt_film_geometry_tile_bounds(const int32_t clip[4], const float filter_radius[2], const int32_t sample_bounds[4],
                                    int32_t out[4], int64_t *pixel_count);
 /*
+ * [UTIL] sample routing for a row-sharded film: a source that holds the nominal sample rows
+ * [src_rows[0], src_rows[1]) of a pixel-major stream over `sample_bounds` owes shard g of `nranks` the rows
+ * out_rows[2g] .. out_rows[2g+1] (its own row block plus floor(r.y + .5) halo rows either side, clipped; empty when
+ * equal).  In a pixel-major stream that is one contiguous run of samples starting at
+ * (out_rows[2g] - src_rows[0]) * width * spp; rows within the halo of a shard edge belong to two runs.  Host
+ * arithmetic only; the exchange itself is the caller's (pbrt_b200/dist.py:route_samples uses NCCL send / recv).
+ */
+int pbrt_film_route_plan(const int32_t sample_bounds[4], const int32_t cropped[4], const float filter_radius[2],
+                         int32_t nranks, const int32_t src_rows[2], int32_t out_rows[]);
+/*
  * [T1] Film::merge_film_tile (film.rs:313-326).  `rgbw` is the tile's Vec<FilmTilePixel>
  * (film.rs:39-42): 4 floats per pixel {contrib_sum.rgb, filter_weight_sum}, row-major over
  * `tile_bounds`.  The tile is consumed by value in the reference, so the buffer is only read.

@@ -77,6 +77,7 @@ PROTOTYPES = {
     "pbrt_film_tile_bounds": (C.c_int, [_vp, _i32p, _i32p, _i64p]),
     "pbrt_film_geometry": (C.c_int, [C.c_int32, C.c_int32, _f32p, _f32p, C.c_float, C.c_int, C.c_int, _i32p, _i32p, _i32p, _f32p]),
     "pbrt_film_geometry_tile_bounds": (C.c_int, [_i32p, _f32p, _i32p, _i32p, _i64p]),
+    "pbrt_film_route_plan": (C.c_int, [_i32p, _i32p, _f32p, C.c_int32, _i32p, _i32p]),
     "pbrt_film_merge_tile": (C.c_int, [_vp, _i32p, _vp, C.c_int]),
     "pbrt_film_merge_tiles": (C.c_int, [_vp, C.c_int32, _i32p, _i64p, _vp, C.c_int64, C.c_int]),
     "pbrt_film_add_samples_tile": (C.c_int, [_vp, _i32p, C.c_int32, _vp, _vp, C.c_int, C.c_int]),

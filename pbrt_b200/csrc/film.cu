@@ -525,6 +525,28 @@ extern "C" int pbrt_film_geometry_tile_bounds(const int32_t clip[4], const float
     return pbrt_film_tile_bounds(&geo, sb, out, pixel_count);
 }
 
+// [UTIL] Routing of a pixel-major stream to row shards.  A source that holds the nominal sample rows
+// [src_rows[0], src_rows[1]) owes shard g the rows of its own block plus the halo h = floor(r.y + .5) on either side,
+// clipped to the sample bounds: in a pixel-major stream that is ONE contiguous run of samples, and a row within h of a
+// shard edge simply belongs to two runs.  No device work: the exchange is nranks sends of slices of the source buffer.
+extern "C" int pbrt_film_route_plan(const int32_t sample_bounds[4], const int32_t cropped[4], const float radius[2],
+                                    int32_t nranks, const int32_t src_rows[2], int32_t out_rows[]) {
+    if (!sample_bounds || !cropped || !radius || !src_rows || !out_rows) return fail(PBRT_E_INVALID, "null argument");
+    if (nranks < 1) return fail(PBRT_E_INVALID, "nranks %d", nranks);
+    const int64_t y0 = cropped[1], H = (int64_t)cropped[3] - cropped[1];
+    const int h = (int)floorf(radius[1] + 0.5f);
+    for (int g = 0; g < nranks; ++g) {
+        // the same split pbrt_film_create_sharded makes
+        const int64_t oy0 = y0 + H * g / nranks, oy1 = y0 + H * (g + 1) / nranks;
+        int64_t a = std::max<int64_t>(std::max<int64_t>(oy0 - h, sample_bounds[1]), src_rows[0]);
+        int64_t b = std::min<int64_t>(std::min<int64_t>(oy1 + h, sample_bounds[3]), src_rows[1]);
+        if (oy1 <= oy0 || b < a) b = a;  // an empty shard needs nothing
+        out_rows[2 * g] = (int32_t)a;
+        out_rows[2 * g + 1] = (int32_t)b;
+    }
+    return PBRT_OK;
+}
+
 // ===================================================================== kernels: merge
 
 // One tile: film.rs:317-325.  16 B tile read + 16 B film read + 16 B film write per pixel.

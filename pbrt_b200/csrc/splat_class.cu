@@ -789,6 +789,8 @@ static int class_pick_width(const ClassParams &CP) {
 int launch_splat_class(PbrtFilm *f, const SplatParams &P, int mode) {
     if (!f->class_bytes || P.tiles || class_env_int("PBRT_B200_NO_CLASS", 0)) return -1;
     if (mode != PBRT_SPLAT_EXACT && mode != PBRT_SPLAT_FMA) return -1;
+    // the per-index class masks cover 32 sample indices; longer pixel runs keep the window kernel's narrower strips
+    if (P.spp > 32 && !class_env_int("PBRT_B200_CLASS_ANY_SPP", 0)) return -1;
     ClassGeom g;
     if (!class_geom(P.rx, P.ry, &g) || g.H != f->class_h) return -1;
     ClassParams CP;

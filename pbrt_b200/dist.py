@@ -37,6 +37,77 @@ def shard_sample_bounds(sample_bounds: Bounds2i, owned_rows: Tuple[int, int], ra
     return Bounds2i.raw(sample_bounds.p_min.x, y0, sample_bounds.p_max.x, max(y0, y1))
 
 
+def route_plan(sample_bounds: Bounds2i, cropped: Bounds2i, radius, nranks: int, src_rows: Tuple[int, int]) -> List[Tuple[int, int]]:
+    """Rows of a source's block that each shard needs (own rows + halo); see pbrt_film_route_plan."""
+    import ctypes as C
+
+    from . import _lib
+
+    out = (C.c_int32 * (2 * nranks))()
+    _lib.check(_lib.lib.pbrt_film_route_plan(_lib.i32x4(sample_bounds.as4()), _lib.i32x4(cropped.as4()),
+                                             (C.c_float * 2)(float(radius[0]), float(radius[1])), int(nranks),
+                                             (C.c_int32 * 2)(int(src_rows[0]), int(src_rows[1])), out))
+    return [(out[2 * g], out[2 * g + 1]) for g in range(nranks)]
+
+
+def route_samples(xy, rgbw, src_rows: Tuple[int, int], sample_bounds: Bounds2i, spp: int, cropped: Bounds2i, radius,
+                  rank: int, nranks: int, group=None):
+    """Route pixel-major sample streams to the row shards that own them.
+
+    Every rank passes the block it holds: torch tensors `xy` (n, 2) and `rgbw` (n, 4) with the samples of nominal rows
+    [src_rows[0], src_rows[1]) of the global stream over `sample_bounds` (n = rows * width * spp; an empty block is
+    fine).  The blocks of all ranks must partition the rows of `sample_bounds`.  Returns (xy, rgbw, bounds): this rank's
+    shard stream — its own rows plus the halo, assembled in row order — ready for Film.add_samples_tile(bounds, ...).
+
+    A row is one contiguous run of a pixel-major stream, so "bucket by owning shard" is a slice per destination and
+    the duplication of rows within the halo of a shard edge is two overlapping slices: no kernel, no staging copy, one
+    group of point-to-point sends (NCCL over NVLink on GPUs, gloo in the CPU tests).  Per-pixel order is unchanged, so a
+    routed render is bit-identical to the single film."""
+    import torch
+    import torch.distributed as dist
+
+    width = sample_bounds.p_max.x - sample_bounds.p_min.x
+    per_row = width * spp
+    assert xy.shape[0] == (src_rows[1] - src_rows[0]) * per_row and rgbw.shape[0] == xy.shape[0]
+    # everybody's block
+    mine = torch.tensor([int(src_rows[0]), int(src_rows[1])], dtype=torch.int64, device=xy.device)
+    if nranks > 1:
+        blocks = [torch.empty_like(mine) for _ in range(nranks)]
+        dist.all_gather(blocks, mine, group=group)
+        blocks = [(int(b[0]), int(b[1])) for b in blocks]
+    else:
+        blocks = [(int(src_rows[0]), int(src_rows[1]))]
+    need = route_plan(sample_bounds, cropped, radius, nranks, (sample_bounds.p_min.y, sample_bounds.p_max.y))[rank]
+    out_rows = need[1] - need[0]
+    oxy = torch.empty((out_rows * per_row, 2), dtype=xy.dtype, device=xy.device)
+    orgbw = torch.empty((out_rows * per_row, 4), dtype=rgbw.dtype, device=rgbw.device)
+    ops, local = [], None
+    send = route_plan(sample_bounds, cropped, radius, nranks, src_rows)
+    for g in range(nranks):  # what I owe shard g
+        a, b = send[g]
+        if b <= a:
+            continue
+        lo, hi = (a - src_rows[0]) * per_row, (b - src_rows[0]) * per_row
+        if g == rank:
+            local = (a, b, lo, hi)
+        else:
+            ops += [dist.P2POp(dist.isend, xy[lo:hi], g, group), dist.P2POp(dist.isend, rgbw[lo:hi], g, group)]
+    for s in range(nranks):  # what source s owes me
+        a, b = route_plan(sample_bounds, cropped, radius, nranks, blocks[s])[rank]
+        if b <= a:
+            continue
+        lo, hi = (a - need[0]) * per_row, (b - need[0]) * per_row
+        if s == rank:
+            oxy[lo:hi].copy_(xy[local[2]:local[3]])
+            orgbw[lo:hi].copy_(rgbw[local[2]:local[3]])
+        else:
+            ops += [dist.P2POp(dist.irecv, oxy[lo:hi], s, group), dist.P2POp(dist.irecv, orgbw[lo:hi], s, group)]
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    return oxy, orgbw, Bounds2i.raw(sample_bounds.p_min.x, need[0], sample_bounds.p_max.x, max(need[0], need[1]))
+
+
 def all_rows(cropped: Bounds2i, nranks: int) -> List[Tuple[int, int]]:
     return [shard_rows(cropped, r, nranks) for r in range(nranks)]
 

@@ -88,3 +88,65 @@ def test_shard_helpers(pb):
     sb = pdist.shard_sample_bounds(c, rows[3], 2.0)
     assert sb.p_min.y == rows[3][0] - 2 and sb.p_max.y == rows[3][1] + 2
     assert pdist.shard_sample_bounds(c, rows[0], 2.0).p_min.y == 10
+
+
+# ------------------------------------------------------------------ sample routing
+
+def _route_worker(rank, world, port, res, spp, blocks, out_dir):
+    sys.path.insert(0, str(ROOT))
+    sys.path.insert(0, str(ROOT / "tests"))
+    import torch
+    import torch.distributed as dist
+
+    import oracle
+    from pbrt_b200 import dist as pdist
+    from pbrt_b200.geometry import Bounds2i
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    o = oracle.load()
+    W, H = res
+    cropped = Bounds2i.raw(0, 0, W, H)
+    sb = Bounds2i.raw(-2, -2, W + 2, H + 2)          # get_sample_bounds of a radius-2 filter
+    xy_all, rgbw_all = oracle.synth_samples(o, sb.as4(), spp, 1)
+    per_row = (W + 4) * spp
+    a, b = blocks[rank]                               # the rows this rank happens to hold
+    lo, hi = (a - sb.p_min.y) * per_row, (b - sb.p_min.y) * per_row
+    xy, rgbw, got_sb = pdist.route_samples(torch.from_numpy(xy_all[lo:hi].copy()), torch.from_numpy(rgbw_all[lo:hi].copy()),
+                                           (a, b), sb, spp, cropped, (2.0, 2.0), rank, world)
+    y0, y1 = pdist.shard_rows(cropped, rank, world)
+    want_sb = pdist.shard_sample_bounds(sb, (y0, y1), 2.0)
+    assert got_sb.as4() == want_sb.as4(), (got_sb.as4(), want_sb.as4())
+    wlo, whi = (want_sb.p_min.y - sb.p_min.y) * per_row, (want_sb.p_max.y - sb.p_min.y) * per_row
+    assert np.array_equal(xy.numpy().view(np.uint32), xy_all[wlo:whi].view(np.uint32))
+    assert np.array_equal(rgbw.numpy().view(np.uint32), rgbw_all[wlo:whi].view(np.uint32))
+    open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,blocks", [
+    (2, [(-2, 42), (42, 42)]),              # rank 0 holds the whole stream
+    (3, [(-2, 9), (9, 10), (10, 42)]),      # uneven blocks that do not line up with the shards
+    (3, [(30, 42), (-2, 5), (5, 30)]),      # blocks in a different order than the shards
+])
+def test_route_samples_delivers_each_shard_its_rows_and_halo(orc, tmp_path, world, blocks):
+    import torch.multiprocessing as mp
+
+    port = _free_port()
+    mp.spawn(_route_worker, args=(world, port, (24, 40), 2, blocks, str(tmp_path)), nprocs=world, join=True)
+    assert all((tmp_path / f"ok{r}").exists() for r in range(world))
+
+
+def test_route_plan_matches_shard_sample_bounds(pb):
+    from pbrt_b200 import dist as pdist
+
+    c = pb.Bounds2i.raw(0, 10, 100, 110)
+    sb = pb.Bounds2i.raw(-4, 6, 104, 114)
+    for n in (1, 2, 3, 8):
+        plan = pdist.route_plan(sb, c, (4.0, 4.0), n, (sb.p_min.y, sb.p_max.y))
+        for g in range(n):
+            want = pdist.shard_sample_bounds(sb, pdist.shard_rows(c, g, n), 4.0)
+            assert plan[g] == (want.p_min.y, want.p_max.y)
+    # a source holding rows [20, 30) owes a far shard nothing
+    assert all(b == a for a, b in pdist.route_plan(sb, c, (4.0, 4.0), 8, (20, 30))[4:])
