@@ -217,6 +217,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--extras", action="store_true", help="(default at N=1) also time the Tier-1 merge / resolve / texture kernels")
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--no-render-c5", action="store_true", help="skip the strong-scaled full render of BASELINE configs[4]")
+    ap.add_argument("--render-passes", type=int, default=16, help="16-spp passes of the configs[4] render (16 = 256 spp)")
     args = ap.parse_args()
 
     # Rank 0 must print exactly one line on stdout.  Libraries (NCCL prints its version on first use)
@@ -326,7 +328,8 @@ def main():
     achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
     roofline = {
         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-        "traffic": measured_traffic(args.workload, args.mode) if world == 1 else None, "peak_source": peak_src, "kernel": "splat_window_kernel" if args.mode != "atomic" else "splat_atomic_kernel",
+        "traffic": measured_traffic(args.workload, args.mode) if world == 1 else None, "peak_source": peak_src,
+        "kernel": "splat_atomic_kernel" if args.mode == "atomic" else ("splat_class_kernel" if wl["radius"][0] in (2.0, 4.0) and spp <= 32 else "splat_window_kernel"),
         "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kern_ms, "kernel_ms_min": min(per_step),
         "note": "24 B/sample read + 32 B/film pixel RMW per launch; the splat is bound by shared-memory load latency and instruction issue, not by HBM (DESIGN.md section 5, profiles/)",
     }
@@ -358,6 +361,14 @@ def main():
     frame2 = fx.assemble(1.0)
     assemble_identical = bool(torch.equal(frame2, frame))
     fx.close()
+
+    # ---- BASELINE configs[4], the whole render, strong-scaled, one timed region ----------------
+    render = None
+    if not args.no_render_c5 and args.mode != "atomic":
+        try:
+            render = render_c5(pb, pdist, synth, torch, dist, stream, rank, world, mode, args.render_passes)
+        except Exception as e:  # the headline line must still be printed
+            render = {"error": f"{type(e).__name__}: {e}"}
 
     # ---- end to end through the public API with host buffers ------------------------------
     e2e = None
@@ -436,6 +447,7 @@ def main():
             "assemble": {"resolve_then_nccl_allgather_ms": assemble_ms, "fused_resolve_peer_store_ms": assemble_fused_ms,
                          "frames_identical": assemble_identical, "bytes_per_rank": max(owned.area(), 0) * 12 * world},
             "percent_of_hbm_peak": 100.0 * achieved / peak,
+            "render_c5": render,
         }
         if extras:
             out["extras"] = extras
@@ -447,6 +459,87 @@ def main():
         emit(out)
     if world > 1:
         dist.destroy_process_group()
+
+
+def render_c5(pb, pdist, synth, torch, dist, stream, rank, world, mode, passes=16):
+    """BASELINE configs[4] end to end on the device, STRONG-scaled: the 7680x4320 film row-sharded over `world` GPUs, Lanczos-sinc
+    r=4, 256 spp as `passes` pixel-major passes of 16 spp, then the final assembly (fused resolve + NVLink peer stores into
+    every rank's full frame) — all inside ONE timed region, device time, max over ranks.  Every pass re-reads the same
+    resident 16-spp stream of the shard (12.7 GB at N=1, far above L2): the work per pass is that of a fresh stream, and the
+    204 GB of 256 distinct spp would not fit.  At N>1 the block also times one-to-all routing of a pass held by rank 0."""
+    W, H, spp = 7680, 4320, 16
+    filt = pb.LanczosSincFilter((4.0, 4.0), 3.0)
+    film = pb.Film.new([W, H], [[0, 0], [1, 1]], filt, 35.0, "render_c5.pfm", 1.0, float("inf"), rank=rank, nranks=world)
+    cropped, owned = film.cropped_pixel_bounds, film.owned_pixel_bounds
+    sb = pdist.shard_sample_bounds(cropped, (owned.p_min.y, owned.p_max.y), 4.0)
+    xy_d, rgbw_d, n_local = synth.samples(sb.as4(), spp, seed=1, index_bounds=cropped.as4())
+    sbl = [[sb.p_min.x, sb.p_min.y], [sb.p_max.x, sb.p_max.y]]
+    fx = pdist.FrameExchange(film)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    film.add_samples_tile(sbl, spp, xy_d, rgbw_d, mode)   # warm-up: one pass and one assembly
+    fx.assemble(1.0)
+    film.clear()
+    barrier()
+    e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    launches0 = pb.launch_count()
+    e[0].record(stream)
+    for _ in range(passes):
+        film.add_samples_tile(sbl, spp, xy_d, rgbw_d, mode)
+    e[1].record(stream)
+    fx.launch(1.0)
+    e[2].record(stream)
+    barrier()                                              # every peer's stores have landed: all frames complete
+    launches = pb.launch_count() - launches0
+    film.check()
+    t = torch.tensor([e[0].elapsed_time(e[2]), e[0].elapsed_time(e[1]), e[1].elapsed_time(e[2])], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, splat_ms, assemble_ms = (float(v) for v in t)
+    n_total = W * H * spp * passes
+    out = {"workload": "7680x4320 film, Lanczos-sinc r=4, %d spp as %d pixel-major passes of 16 (BASELINE configs[4]), rows sharded over %d GPU(s), "
+                       "then fused resolve + peer-store assembly of the full frame on every rank" % (spp * passes, passes, world),
+           "scaling": "strong", "n_gpus": world, "ms": total_ms, "splat_ms": splat_ms, "assemble_ms": assemble_ms,
+           "assemble_share": assemble_ms / total_ms, "samples": n_total, "samples_per_s": n_total / (total_ms * 1e-3),
+           "gpu_launches": int(launches), "mode": {pb.SPLAT_EXACT: "exact", pb.SPLAT_FMA: "fma"}.get(mode, str(mode)),
+           "samples_per_rank_per_pass_incl_halo": n_local, "timing": "CUDA events on the launching stream, max over ranks",
+           "note": "each pass re-reads the same resident 16-spp stream (exceeds L2)"}
+    fx.close()
+    if world > 1:
+        # one-to-all routing: rank 0 holds a whole 16-spp pass of a 1920-row band and routes it to the owning shards
+        from pbrt_b200.dist import _DeviceArray
+        band = pb.Bounds2i.raw(0, 0, W, 1080)
+        bsb = pb.Bounds2i.raw(-4, -4, W + 4, 1084)
+        if rank == 0:
+            bxy_d, brgbw_d, bn = synth.samples(bsb.as4(), spp, seed=1)
+            bxy = torch.as_tensor(_DeviceArray(bxy_d.ptr, (bn, 2)), device="cuda")
+            brgbw = torch.as_tensor(_DeviceArray(brgbw_d.ptr, (bn, 4)), device="cuda")
+            rows = (bsb.p_min.y, bsb.p_max.y)
+        else:
+            bn = 0
+            bxy = torch.empty((0, 2), dtype=torch.float32, device="cuda")
+            brgbw = torch.empty((0, 4), dtype=torch.float32, device="cuda")
+            rows = (bsb.p_max.y, bsb.p_max.y)
+        pdist.route_samples(bxy, brgbw, rows, bsb, spp, band, (4.0, 4.0), rank, world)   # warm-up (NCCL channels)
+        barrier()
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        r0.record(stream)
+        lxy, lrgbw, lsb = pdist.route_samples(bxy, brgbw, rows, bsb, spp, band, (4.0, 4.0), rank, world)
+        r1.record(stream)
+        barrier()
+        rt = torch.tensor([r0.elapsed_time(r1)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(rt, op=dist.ReduceOp.MAX)
+        n_band = bsb.area() * spp
+        out["route_one_to_all"] = {"ms": float(rt.item()), "samples": n_band, "samples_per_s": n_band / (float(rt.item()) * 1e-3),
+                                   "bytes_from_rank0": int(n_band * 24 * (world - 1) / world),
+                                   "note": "7688x1088-pixel band, 16 spp, all on rank 0; route_samples = NCCL send/recv of row slices, halo rows sent to both neighbours"}
+        del lxy, lrgbw
+    film.close()
+    return out
 
 
 def time_extras(pb, synth, film, torch, stream, peak, xy_main=None, rgbw_main=None, spp_main=16):
