@@ -13,6 +13,10 @@ pub struct PbrtFilm {
 pub const PBRT_OK: c_int = 0;
 pub const PBRT_E_RANGE: c_int = 3;
 pub const PBRT_SPLAT_EXACT: c_int = 0;
+pub const PBRT_SPLAT_FMA: c_int = 1;
+pub const PBRT_MEM_HOST: c_int = 0;
+pub const PBRT_MEM_DEVICE: c_int = 1;
+pub const PBRT_MEM_PINNED_ASYNC: c_int = 2;
 
 extern "C" {
     pub fn pbrt_b200_init(device: c_int) -> c_int;
@@ -52,6 +56,14 @@ extern "C" {
         sample_bounds: *const i32,
         out: *mut i32,
         pixel_count: *mut i64,
+    ) -> c_int;
+    pub fn pbrt_film_route_plan(
+        sample_bounds: *const i32,
+        cropped: *const i32,
+        filter_radius: *const c_float,
+        nranks: i32,
+        src_rows: *const i32, // [2]
+        out_rows: *mut i32,   // [2 * nranks]
     ) -> c_int;
     pub fn pbrt_film_merge_tile(film: *mut PbrtFilm, tile_bounds: *const i32, rgbw: *const c_float, src_is_device: c_int) -> c_int;
     pub fn pbrt_film_add_samples_tile(

@@ -3,6 +3,12 @@
 //! Drop-in replacement for the reference's src/core/film.rs (install it under that name): every `pub` item keeps its signature
 //! (reference lines cited), the pixel storage moves to HBM behind a `PbrtFilm*`, and both hot loops
 //! (`merge_film_tile` :313-326, `write_image` :340-372) become one FFI call each.
+//!
+//! EXTENSION: `FilmTile::add_sample` — the method the fields at film.rs:428-436 were declared for and the reference never
+//! wrote (pbrt-v3 7.9.2).  It buffers the sample on the host; `merge_film_tile` hands the tile's samples to the device in
+//! one call (`pbrt_film_add_samples_tile` when they arrived in pixel-major order — the order a renderer's tile loop
+//! produces, which the exact, order-preserving kernel needs — else the order-free scatter) before merging the tile's own
+//! pixels, and then asks `pbrt_film_check` whether a sample broke the kernel's contract.
 use log::info;
 
 use crate::{
@@ -111,18 +117,42 @@ impl Film {
         ffi::check(unsafe { ffi::pbrt_film_tile_bounds(self.handle, b4(&sample_bounds).as_ptr(), tb.as_mut_ptr(), &mut n) });
         FilmTile {
             pixel_bounds: from_b4(tb),
-            _filter_radius: self.filter.radius(),
-            _inv_filter_radius: self.filter.inv_radius(),
-            _filter_table: &self.filter_table,
-            _filter_table_size: FILTER_TABLE_WIDTH,
-            _max_sample_luminance: self.max_sample_luminance,
+            filter_radius: self.filter.radius(),
+            inv_filter_radius: self.filter.inv_radius(),
+            filter_table: &self.filter_table,
+            filter_table_size: FILTER_TABLE_WIDTH,
+            max_sample_luminance: self.max_sample_luminance,
             pixels: vec![FilmTilePixel::default(); n as usize],
+            sample_bounds,
+            sample_xy: Vec::new(),
+            sample_rgbw: Vec::new(),
         }
     }
 
     /// film.rs:313-326 — the loop is `merge_tile_kernel`; the tile is consumed by value as before
     pub fn merge_film_tile(&self, tile: FilmTile) {
         info!("Merging film tile {}", tile.pixel_bounds);
+        if !tile.sample_xy.is_empty() {
+            // EXTENSION: the samples recorded through FilmTile::add_sample, splatted and merged on the device
+            let sb = b4(&tile.sample_bounds);
+            match tile.pixel_major_spp() {
+                Some(spp) => ffi::check(unsafe {
+                    ffi::pbrt_film_add_samples_tile(
+                        self.handle, sb.as_ptr(), spp as i32, tile.sample_xy.as_ptr() as *const Float,
+                        tile.sample_rgbw.as_ptr() as *const Float, ffi::PBRT_MEM_HOST, ffi::PBRT_SPLAT_EXACT,
+                    )
+                }),
+                None => ffi::check(unsafe {
+                    ffi::pbrt_film_add_samples(
+                        self.handle, sb.as_ptr(), tile.sample_xy.len() as u64, tile.sample_xy.as_ptr() as *const Float,
+                        tile.sample_rgbw.as_ptr() as *const Float, ffi::PBRT_MEM_HOST,
+                    )
+                }),
+            }
+            // a sample outside its nominal pixel / non-finite radiance is a programming error: panic like the
+            // reference's debug_assert! / unwrap would (film.rs:391-401)
+            ffi::check(unsafe { ffi::pbrt_film_check(self.handle) });
+        }
         ffi::check(unsafe {
             ffi::pbrt_film_merge_tile(self.handle, b4(&tile.pixel_bounds).as_ptr(), tile.pixels.as_ptr() as *const Float, 0)
         });
@@ -156,20 +186,59 @@ impl Drop for Film {
     }
 }
 
-/// film.rs:428-436 — unchanged layout; `pixels` is what merge_film_tile hands to the device
+/// film.rs:428-436 — the reference's fields (its `_`-prefixed ones are in use here) plus the sample buffers of
+/// `add_sample`; `pixels` is what merge_film_tile hands to the device
 pub struct FilmTile<'ft> {
     pixel_bounds: Bounds2i,
-    _filter_radius: Vector2f,
-    _inv_filter_radius: Vector2f,
-    _filter_table: &'ft Vec<Float>,
-    _filter_table_size: usize,
-    _max_sample_luminance: Float,
+    filter_radius: Vector2f,
+    inv_filter_radius: Vector2f,
+    filter_table: &'ft Vec<Float>,
+    filter_table_size: usize,
+    max_sample_luminance: Float,
     pixels: Vec<FilmTilePixel>,
+    sample_bounds: Bounds2i,          // what get_film_tile was asked for: the nominal pixels that will carry samples
+    sample_xy: Vec<[Float; 2]>,       // p_film of every add_sample call, in call order
+    sample_rgbw: Vec<[Float; 4]>,     // {L.rgb, sample_weight}
 }
 
 impl<'ft> FilmTile<'ft> {
     /// film.rs:461-463
     pub fn get_pixel_bounds(&self) -> Bounds2i { self.pixel_bounds }
+
+    /// EXTENSION — pbrt-v3 `FilmTile::AddSample(pFilm, L, sampleWeight)`.  O(1) on the host: the filter footprint, the
+    /// table lookups and the accumulation (App. A.1 of SURVEY.md) run on the device when the tile is merged.  The
+    /// luminance clamp uses `max_sample_luminance`, the footprint `filter_radius` / `inv_filter_radius` and the
+    /// `filter_table_size`² entries of `filter_table` — all of which the film's device object already holds.
+    pub fn add_sample(&mut self, p_film: Point2f, l: Spectrum, sample_weight: Float) {
+        debug_assert!(self.filter_table.len() == self.filter_table_size * self.filter_table_size);
+        debug_assert!(self.filter_radius.x * self.inv_filter_radius.x == 1. && self.max_sample_luminance >= 0.);
+        let c: [Float; 3] = l.into(); // RGBSpectrum -> [r, g, b] (spectrum.rs:155-189)
+        self.sample_xy.push([p_film.x, p_film.y]);
+        self.sample_rgbw.push([c[0], c[1], c[2], sample_weight]);
+    }
+
+    /// `Some(spp)` when the recorded samples are pixel-major over `sample_bounds`: pixels row-major, the same number of
+    /// samples for every pixel, each sample inside its pixel — the shape `pbrt_film_add_samples_tile` takes.
+    fn pixel_major_spp(&self) -> Option<usize> {
+        let (w, h) = (
+            (self.sample_bounds.p_max.x - self.sample_bounds.p_min.x).max(0) as usize,
+            (self.sample_bounds.p_max.y - self.sample_bounds.p_min.y).max(0) as usize,
+        );
+        let n = self.sample_xy.len();
+        if w * h == 0 || n == 0 || n % (w * h) != 0 {
+            return None;
+        }
+        let spp = n / (w * h);
+        for (i, p) in self.sample_xy.iter().enumerate() {
+            let pixel = i / spp;
+            let px = (self.sample_bounds.p_min.x + (pixel % w) as isize) as Float;
+            let py = (self.sample_bounds.p_min.y + (pixel / w) as isize) as Float;
+            if !(p[0] >= px && p[0] <= px + 1. && p[1] >= py && p[1] <= py + 1.) {
+                return None;
+            }
+        }
+        Some(spp)
+    }
 
     /// film.rs:465-476
     fn pixel_offset(&self, p: Point2i) -> usize {
