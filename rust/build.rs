@@ -10,7 +10,7 @@ fn main() {
     let root = PathBuf::from(env::var("PBRT_B200_ROOT").unwrap_or_else(|_| "../".into()));
     let nvcc = env::var("NVCC").unwrap_or_else(|_| "/usr/local/cuda/bin/nvcc".into());
     let mut objs = Vec::new();
-    for src in ["film.cu", "splat.cu"] {
+    for src in ["film.cu", "splat.cu", "splat_class.cu"] {
         let obj = out.join(src).with_extension("o");
         let status = Command::new(&nvcc)
             .args(["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo"])
