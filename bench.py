@@ -624,17 +624,28 @@ def time_extras(pb, synth, film, torch, stream, peak, xy_main=None, rgbw_main=No
         del xy_t, rgbw_t, sidx, order
     except Exception as e:
         out["splat_tiles_16x16"] = {"error": f"{type(e).__name__}: {e}"}
-    # a14: 1e8 lookups
+    # a14: 1e8 lookups, alternating between two buffers so that no launch finds its lines in L2 (2 x 400 MB, 2 x 1.2 GB)
     n = 100_000_000
-    t1 = torch.empty(n, dtype=torch.float32, device="cuda")
+    t1 = [torch.empty(n, dtype=torch.float32, device="cuda") for _ in range(2)]
     tex = pb.ConstantTexture(10.0)
-    ms = timed(lambda: tex.evaluate_batch(n, out=t1))
+    turn = [0]
+
+    def alt(bufs, fn):
+        turn[0] ^= 1
+        fn(bufs[turn[0]])
+
+    ms = timed(lambda: alt(t1, lambda b: tex.evaluate_batch(n, out=b)))
     out["texture_constant_f32"] = entry(n, 4, ms, "lookups_per_s")
+    ms = timed(lambda: alt(t1, lambda b: b.fill_(10.0)))
+    out["texture_constant_f32"]["torch_fill_GB/s"] = n * 4 / (ms * 1e-3) / 1e9
     del t1
-    t3 = torch.empty((n, 3), dtype=torch.float32, device="cuda")
+    t3 = [torch.empty((n, 3), dtype=torch.float32, device="cuda") for _ in range(2)]
     tex3 = pb.ConstantTexture((1.0, 0.0, 0.0))
-    ms = timed(lambda: tex3.evaluate_batch(n, out=t3))
+    ms = timed(lambda: alt(t3, lambda b: tex3.evaluate_batch(n, out=b)))
     out["texture_constant_rgb"] = entry(n, 12, ms, "lookups_per_s")
+    ms = timed(lambda: alt(t3, lambda b: b.fill_(1.0)))
+    out["texture_constant_rgb"]["torch_fill_GB/s"] = n * 12 / (ms * 1e-3) / 1e9
+    out["texture_note"] = "two output buffers alternated per launch (working set 2 x 400 MB / 2 x 1.2 GB >> 126 MB L2); torch_fill = eager torch.Tensor.fill_ on the same buffers"
     return out
 
 

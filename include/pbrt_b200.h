@@ -179,7 +179,11 @@ int pbrt_film_merge_tiles(PbrtFilm *film, int32_t ntiles, const int32_t *tile_bo
  * Per pixel the samples are accumulated in stream order, then converted and added to the film
  * exactly as merge_film_tile does.  Radiance must be finite (pbrt zeroes non-finite samples before
  * AddSample); violations of either contract are reported by pbrt_film_check and leave the film
- * contents undefined.
+ * contents undefined.  Non-finite radiance is detected where it lands: in every mode a pixel sum that became
+ * inf / NaN sets PBRT_E_NONFINITE (a sample whose footprint misses the film entirely goes unnoticed, and unharmed).
+ * Radius 2 or 4 on both axes (triangle, gaussian, mitchell, lanczos defaults) with at most 32 samples per pixel
+ * per call runs the phase-class kernel (splat_class.cu); other radii the window kernel; radii beyond 4 pixels
+ * or unequal on the two axes a generic gather.  All three give identical results.
  */
 enum { PBRT_SPLAT_EXACT = 0,   /* gather, mul then add: bit-identical to the CPU restatement */
        PBRT_SPLAT_FMA = 1,     /* gather, same order, fused multiply-add */

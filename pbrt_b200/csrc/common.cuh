@@ -113,6 +113,9 @@ struct PbrtFilm {
     int64_t idx_need;        // pixels the batch's rgbw buffer must hold
     void *d_tile_desc;       // add_samples_tiles: SplatTile array (grow-only)
     size_t tile_desc_bytes;
+    void *h_tile_desc;       // its page-locked host staging copy: the upload is asynchronous, ...
+    cudaEvent_t ev_tile_desc;  // ... and this event says when the staging copy may be overwritten
+    bool tile_desc_event;
     // PBRT_MEM_PINNED_ASYNC inputs: two staging sets filled on the copy stream while the other is consumed
     void *d_pipe[2][4];      // [set][0 = xy, 1 = rgbw, 2 = rgb, 3 = sample weights]
     size_t pipe_bytes[2][4];

@@ -420,6 +420,8 @@ extern "C" int pbrt_film_destroy(PbrtFilm *f) {
     cudaFree(f->d_scratch_tile);
     cudaFree(f->d_idx);
     cudaFree(f->d_tile_desc);
+    if (f->h_tile_desc) cudaFreeHost(f->h_tile_desc);
+    if (f->tile_desc_event) cudaEventDestroy(f->ev_tile_desc);
     cudaFree(f->d_class);
     for (int i = 0; i < 2; ++i) {
         for (int k = 0; k < 4; ++k) cudaFree(f->d_pipe[i][k]);
@@ -648,8 +650,15 @@ static bool inside(const Bounds &outer, const Bounds &b) {
     return b.x0 >= outer.x0 && b.y0 >= outer.y0 && b.x1 <= outer.x1 && b.y1 <= outer.y1;
 }
 
+// entry points that take host or device memory only (PBRT_MEM_PINNED_ASYNC is for add_samples_tile[_rgb] and resolve)
+static int host_or_device(int kind, const char *what) {
+    if (kind == PBRT_MEM_HOST || kind == PBRT_MEM_DEVICE) return PBRT_OK;
+    return fail(PBRT_E_INVALID, "%s: memory kind %d not supported here (PBRT_MEM_HOST or PBRT_MEM_DEVICE)", what, kind);
+}
+
 extern "C" int pbrt_film_merge_tile(PbrtFilm *f, const int32_t tbv[4], const float *rgbw, int src_is_device) {
     PB_API_LOCK;
+    if (int rc = host_or_device(src_is_device, "merge_film_tile")) return rc;
     if (!f || !tbv) return fail(PBRT_E_INVALID, "null argument");
     Bounds tb{tbv[0], tbv[1], tbv[2], tbv[3]};
     // Bounds2i::iter over an inverted or empty box yields nothing (bounds.rs:284-288)
@@ -674,6 +683,7 @@ extern "C" int pbrt_film_merge_tile(PbrtFilm *f, const int32_t tbv[4], const flo
 extern "C" int pbrt_film_merge_tiles(PbrtFilm *f, int32_t ntiles, const int32_t *tbs, const int64_t *offsets,
                                      const float *rgbw, int64_t total_pixels, int src_is_device) {
     PB_API_LOCK;
+    if (int rc = host_or_device(src_is_device, "merge_film_tiles")) return rc;
     if (!f) return fail(PBRT_E_INVALID, "null film");
     if (ntiles <= 0) return PBRT_OK;
     if (!tbs || !offsets || !rgbw) return fail(PBRT_E_INVALID, "null argument");
@@ -978,35 +988,53 @@ struct FrameList {
     int n;
 };
 
+// PPT pixels per thread (pixel j of thread t = base + j*RES_PIX + t), as resolve_kernel: PPT film loads in flight per thread
+template <int PPT>
 __global__ void __launch_bounds__(RES_PIX) resolve_to_frames_kernel(const float4 *__restrict__ xyzw,
                                                                     const float *__restrict__ splat, long long npix,
                                                                     float splat_scale, float scale, FrameList frames,
                                                                     long long frame_offset_px) {
-    __shared__ __align__(16) float s_in[RES_PIX * 3];
-    __shared__ __align__(16) float s_out[RES_PIX * 3];
-    const long long base = (long long)blockIdx.x * RES_PIX;
-    const int n = (int)min((long long)RES_PIX, npix - base);
+    constexpr int TILE = RES_PIX * PPT;
+    __shared__ __align__(16) float s_in[TILE * 3];
+    __shared__ __align__(16) float s_out[TILE * 3];
+    const long long base = (long long)blockIdx.x * TILE;
+    const int n = (int)min((long long)TILE, npix - base);
     const int tid = threadIdx.x;
-    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (tid < n) p = pb::ldg_stream(&xyzw[base + tid]);
-    if (n == RES_PIX) {
+    const bool full = n == TILE;
+    float4 p[PPT];
+#pragma unroll
+    for (int j = 0; j < PPT; ++j) {
+        p[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (full || j * RES_PIX + tid < n) p[j] = pb::ldg_stream(&xyzw[base + j * RES_PIX + tid]);
+    }
+    if (full) {
         const float4 *src = reinterpret_cast<const float4 *>(splat + base * 3);
-        if (tid < RES_PIX * 3 / 4) reinterpret_cast<float4 *>(s_in)[tid] = pb::ldg_stream(&src[tid]);
+#pragma unroll
+        for (int i = 0; i < (TILE * 3 / 4 + RES_PIX - 1) / RES_PIX; ++i)
+            if (i * RES_PIX + tid < TILE * 3 / 4)
+                reinterpret_cast<float4 *>(s_in)[i * RES_PIX + tid] = pb::ldg_stream(&src[i * RES_PIX + tid]);
     } else {
         for (int i = tid; i < n * 3; i += RES_PIX) s_in[i] = splat[base * 3 + i];
     }
     __syncthreads();
-    if (tid < n) {
-        float r, g, b;
-        resolve_pixel(p, s_in[3 * tid], s_in[3 * tid + 1], s_in[3 * tid + 2], splat_scale, scale, r, g, b);
-        s_out[3 * tid] = r; s_out[3 * tid + 1] = g; s_out[3 * tid + 2] = b;
+#pragma unroll
+    for (int j = 0; j < PPT; ++j) {
+        const int q = j * RES_PIX + tid;
+        if (full || q < n) {
+            float r, g, b;
+            resolve_pixel(p[j], s_in[3 * q], s_in[3 * q + 1], s_in[3 * q + 2], splat_scale, scale, r, g, b);
+            s_out[3 * q] = r; s_out[3 * q + 1] = g; s_out[3 * q + 2] = b;
+        }
     }
     __syncthreads();
     const long long o = (frame_offset_px + base) * 3;  // float index in a frame; 16-byte aligned for full blocks
     for (int f = 0; f < frames.n; ++f) {
         float *dst = frames.p[f] + o;
-        if (n == RES_PIX && ((o & 3) == 0)) {
-            if (tid < RES_PIX * 3 / 4) reinterpret_cast<float4 *>(dst)[tid] = reinterpret_cast<float4 *>(s_out)[tid];
+        if (full && ((o & 3) == 0)) {
+#pragma unroll
+            for (int i = 0; i < (TILE * 3 / 4 + RES_PIX - 1) / RES_PIX; ++i)
+                if (i * RES_PIX + tid < TILE * 3 / 4)
+                    reinterpret_cast<float4 *>(dst)[i * RES_PIX + tid] = reinterpret_cast<float4 *>(s_out)[i * RES_PIX + tid];
         } else {
             for (int i = tid; i < n * 3; i += RES_PIX) dst[i] = s_out[i];
         }
@@ -1027,9 +1055,10 @@ extern "C" int pbrt_film_resolve_rgb_to_frames(const PbrtFilm *f, float splat_sc
         fl.p[i] = (float *)frames[i];
     }
     const long long off = (long long)(f->owned.y0 - f->cropped.y0) * pb::bw(f->cropped);
-    int blocks = (int)((f->npix + RES_PIX - 1) / RES_PIX);
-    resolve_to_frames_kernel<<<blocks, RES_PIX, 0, ctx().stream>>>(f->d_xyzw, f->d_splat, (long long)f->npix, splat_scale,
-                                                                   f->scale, fl, off);
+    constexpr int PPT = 2;
+    int blocks = (int)((f->npix + RES_PIX * PPT - 1) / (RES_PIX * PPT));
+    resolve_to_frames_kernel<PPT><<<blocks, RES_PIX, 0, ctx().stream>>>(f->d_xyzw, f->d_splat, (long long)f->npix, splat_scale,
+                                                                        f->scale, fl, off);
     PB_LAUNCH_CHECK("resolve_to_frames_kernel");
     return PBRT_OK;
 }
@@ -1107,7 +1136,7 @@ __global__ void __launch_bounds__(256) scatter_samples_kernel(float4 *__restrict
                                                               const float2 *__restrict__ xy,
                                                               const float4 *__restrict__ rgbw,
                                                               const float *__restrict__ table, float rx, float ry,
-                                                              float irx, float iry, float max_lum) {
+                                                              float irx, float iry, float max_lum, int *__restrict__ err) {
     __shared__ float s_table[256];
     s_table[threadIdx.x] = table[threadIdx.x];
     __syncthreads();
@@ -1124,6 +1153,11 @@ __global__ void __launch_bounds__(256) scatter_samples_kernel(float4 *__restrict
         int p0x = max(__float2int_ru(dx - rx), tb.x0), p0y = max(__float2int_ru(dy - ry), tb.y0);
         int p1x = min(__float2int_rd(dx + rx) + 1, tb.x1), p1y = min(__float2int_rd(dy + ry) + 1, tb.y1);
         float cr = L.x * L.w, cg = L.y * L.w, cb = L.z * L.w;
+        const float z = cr * 0.f + cg * 0.f + cb * 0.f + dx * 0.f + dy * 0.f;  // NaN iff anything is inf or NaN
+        if (z != z) {
+            atomicOr(err, pb::ERRBIT_NONFINITE);
+            continue;
+        }
         const int tw = tb.x1 - tb.x0;
         for (int y = p0y; y < p1y; ++y) {
             int iy = min(__float2int_rd(fabsf(((float)y - dy) * iry * 16.f)), 15);
@@ -1143,6 +1177,7 @@ __global__ void __launch_bounds__(256) scatter_samples_kernel(float4 *__restrict
 extern "C" int pbrt_film_add_samples(PbrtFilm *f, const int32_t sbv[4], uint64_t n, const float *xy, const float *rgbw,
                                      int src_is_device) {
     PB_API_LOCK;
+    if (int rc = host_or_device(src_is_device, "add_samples")) return rc;
     if (!f || !sbv) return fail(PBRT_E_INVALID, "null argument");
     Bounds tb;
     if (int rc = tile_bounds_impl(f, sbv, f->owned, &tb)) return rc;
@@ -1168,7 +1203,7 @@ extern "C" int pbrt_film_add_samples(PbrtFilm *f, const int32_t sbv[4], uint64_t
     PB_CUDA(cudaMemsetAsync(f->d_scratch_tile, 0, px * sizeof(float4), s));  // FilmTilePixel::default()
     int blocks = (int)std::min<uint64_t>((n + 255) / 256, (uint64_t)ctx().sm_count * 16);
     scatter_samples_kernel<<<blocks, 256, 0, s>>>(f->d_scratch_tile, tb, n, d_xy, d_rgbw, f->d_table, f->radius[0],
-                                                  f->radius[1], f->inv_radius[0], f->inv_radius[1], f->max_lum);
+                                                  f->radius[1], f->inv_radius[0], f->inv_radius[1], f->max_lum, f->d_err);
     PB_LAUNCH_CHECK("scatter_samples_kernel");
     dim3 grid((pb::bw(tb) + 255) / 256, std::min(pb::bh(tb), 4096));
     merge_tile_kernel<<<grid, 256, 0, s>>>(f->d_xyzw, f->owned, tb, f->d_scratch_tile);
@@ -1203,6 +1238,7 @@ __global__ void __launch_bounds__(256) add_splats_kernel(float *__restrict__ spl
 
 extern "C" int pbrt_film_add_splats(PbrtFilm *f, uint64_t n, const float *xy, const float *rgb, int src_is_device) {
     PB_API_LOCK;
+    if (int rc = host_or_device(src_is_device, "add_splats")) return rc;
     if (!f) return fail(PBRT_E_INVALID, "null film");
     if (n == 0 || f->npix == 0) return PBRT_OK;
     if (!xy || !rgb) return fail(PBRT_E_INVALID, "null argument");
@@ -1232,6 +1268,7 @@ __global__ void __launch_bounds__(256) set_image_kernel(float4 *__restrict__ xyz
 
 extern "C" int pbrt_film_set_image(PbrtFilm *f, const float *rgb, int src_is_device) {
     PB_API_LOCK;
+    if (int rc = host_or_device(src_is_device, "set_image")) return rc;
     if (!f || !rgb) return fail(PBRT_E_INVALID, "null argument");
     if (f->npix == 0) return PBRT_OK;
     const float *d_rgb = rgb;
@@ -1396,6 +1433,7 @@ extern "C" int pbrt_film_add_samples_tiles(PbrtFilm *f, int32_t ntiles, const in
                                            int32_t spp, const float *xy, const float *rgbw, int64_t total_samples,
                                            int src_is_device, int mode) {
     PB_API_LOCK;
+    if (int rc = host_or_device(src_is_device, "add_samples_tiles")) return rc;
     if (!f) return fail(PBRT_E_INVALID, "null film");
     if (ntiles <= 0) return PBRT_OK;
     if (!sbs || !sample_offsets || !xy || !rgbw) return fail(PBRT_E_INVALID, "null argument");
@@ -1440,15 +1478,25 @@ extern "C" int pbrt_film_add_samples_tiles(PbrtFilm *f, int32_t ntiles, const in
         f->scratch_tile_px = (size_t)total_px;
     }
     const size_t dbytes = desc.size() * sizeof(pb::SplatTile);
+    // descriptors go through a page-locked staging copy owned by the film, so the upload is asynchronous; the event
+    // tells the next call when it may overwrite the staging copy (normally long since)
+    if (f->tile_desc_event) PB_CUDA(cudaEventSynchronize(f->ev_tile_desc));
     if (dbytes > f->tile_desc_bytes) {
         cudaFree(f->d_tile_desc);
-        f->d_tile_desc = nullptr;
+        if (f->h_tile_desc) cudaFreeHost(f->h_tile_desc);
+        f->d_tile_desc = f->h_tile_desc = nullptr;
         f->tile_desc_bytes = 0;
         PB_CUDA(cudaMalloc(&f->d_tile_desc, dbytes + 256));
+        PB_CUDA(cudaMallocHost(&f->h_tile_desc, dbytes + 256));
         f->tile_desc_bytes = dbytes + 256;
     }
-    PB_CUDA(cudaMemcpyAsync(f->d_tile_desc, desc.data(), dbytes, cudaMemcpyHostToDevice, ctx().stream));
-    PB_CUDA(cudaStreamSynchronize(ctx().stream));  // desc is a local
+    if (!f->tile_desc_event) {
+        PB_CUDA(cudaEventCreateWithFlags(&f->ev_tile_desc, cudaEventDisableTiming));
+        f->tile_desc_event = true;
+    }
+    memcpy(f->h_tile_desc, desc.data(), dbytes);
+    PB_CUDA(cudaMemcpyAsync(f->d_tile_desc, f->h_tile_desc, dbytes, cudaMemcpyHostToDevice, ctx().stream));
+    PB_CUDA(cudaEventRecord(f->ev_tile_desc, ctx().stream));
     int rc = pb::launch_splat_tiles(f, ntiles, (const pb::SplatTile *)f->d_tile_desc, max_w, max_h, spp, d_xy, d_rgbw,
                                     f->d_scratch_tile, mode);
     if (rc < 0) {
@@ -1467,59 +1515,40 @@ extern "C" int pbrt_film_add_samples_tiles(PbrtFilm *f, int32_t ntiles, const in
 
 // ===================================================================== kernels: textures, LUT, synthetic inputs
 
-// ConstantTexture<Float>::evaluate x n: 4 B / lookup, write-only (constant.rs:139-141)
-__global__ void __launch_bounds__(256) fill_f32_kernel(float *__restrict__ out, unsigned long long n, float v) {
-    // head (to 16-byte alignment), float4 body, tail
-    const unsigned long long head = min(n, (unsigned long long)((16 - ((uintptr_t)out & 15)) & 15) / 4);
-    const unsigned long long nvec = (n - head) / 4;
-    float4 *body = reinterpret_cast<float4 *>(out + head);
-    const float4 v4 = make_float4(v, v, v, v);
-    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
-    unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < head) out[i] = v;
-    // four independent stores per trip; plain write-back stores (a store-only stream gains nothing from the
-    // no-allocate hint and measured slower with it)
-    for (; i + 3 * stride < nvec; i += 4 * stride) {
-        body[i] = v4; body[i + stride] = v4; body[i + 2 * stride] = v4; body[i + 3 * stride] = v4;
-    }
-    for (; i < nvec; i += stride) body[i] = v4;
-    const unsigned long long done = head + nvec * 4;
-    i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (done + i < n) out[done + i] = v;
-}
-
-// ConstantTexture<Spectrum>::evaluate x n: 12 B / lookup.  The float stream has period 3, so a
-// float4 at vector index k holds value[(4k+j) % 3].
-__global__ void __launch_bounds__(256) fill_rgb_kernel(float *__restrict__ out, unsigned long long n, float r, float g,
-                                                       float b) {
-    const unsigned long long nf = n * 3;
+// ConstantTexture<T>::evaluate x n (constant.rs:139-141): 4 B (Float) or 12 B (Spectrum) per lookup, write-only.
+// No loop: one CTA of 128 threads per 8 KB, four float4 stores per thread, 512 contiguous bytes per warp-store, and the
+// hardware block scheduler does the striding — the shape torch's vectorised fill has, and the one that reaches its
+// bandwidth (a persistent grid-stride version of the same stores stayed 4-6 % below it; tools/fill_bench.py).
+// PERIOD3: the float stream of an rgb fill has period 3, so the float4 at vector index k holds value[(head + 4k + j) % 3]
+// = value[(head + k + j) % 3].  Block 0 also writes the unaligned head (to 16-byte alignment) and the tail.
+template <bool PERIOD3>
+__global__ void __launch_bounds__(128) fill_kernel(float *__restrict__ out, unsigned long long nf, float c0, float c1, float c2) {
     const unsigned long long head = min(nf, (unsigned long long)((16 - ((uintptr_t)out & 15)) & 15) / 4);
     const unsigned long long nvec = (nf - head) / 4;
     float4 *body = reinterpret_cast<float4 *>(out + head);
-    const float c[3] = {r, g, b};
-    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
-    unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < head) out[i] = c[i % 3];
-    // The phase of the first float of vector k is (head + 4k) % 3 = (head + k) % 3.  The launch uses a
-    // multiple of 3 threads, so a thread's phase never changes as it strides: pick its vector once.
-    const unsigned phase = (unsigned)((head + i) % 3);
-    const float4 v = phase == 0 ? make_float4(r, g, b, r) : (phase == 1 ? make_float4(g, b, r, g) : make_float4(b, r, g, b));
-    for (; i + 3 * stride < nvec; i += 4 * stride) {
-        body[i] = v; body[i + stride] = v; body[i + 2 * stride] = v; body[i + 3 * stride] = v;
+    const float4 v0 = make_float4(c0, c1, c2, c0), v1 = make_float4(c1, c2, c0, c1), v2 = make_float4(c2, c0, c1, c2);
+    const unsigned long long base = (unsigned long long)blockIdx.x * 512 + threadIdx.x;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const unsigned long long k = base + j * 128;
+        if (k < nvec) {
+            float4 v = v0;
+            if (PERIOD3) {
+                const unsigned ph = (unsigned)((head + k) % 3);
+                v = ph == 0 ? v0 : (ph == 1 ? v1 : v2);
+            }
+            body[k] = v;
+        }
     }
-    for (; i < nvec; i += stride) body[i] = v;
-    const unsigned long long done = head + nvec * 4;
-    i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (done + i < nf) out[done + i] = c[(done + i) % 3];
+    if (blockIdx.x == 0 && threadIdx.x < 8) {
+        const float c[3] = {c0, c1, c2};
+        const unsigned long long i = threadIdx.x, done = head + nvec * 4;
+        if (i < head) out[i] = c[PERIOD3 ? i % 3 : 0];
+        if (done + i < nf) out[done + i] = c[PERIOD3 ? (done + i) % 3 : 0];
+    }
 }
 
-static int fill_grid(unsigned long long nvec) {
-    unsigned long long want = (nvec + 255) / 256;
-    // measured on B200: 8 CTAs per SM (one resident wave) 0.91 of the copy peak, 64 per SM 1.04-1.07
-    static const int per_sm = getenv("PBRT_B200_FILL_CTAS") ? atoi(getenv("PBRT_B200_FILL_CTAS")) : 64;
-    unsigned long long cap = (unsigned long long)ctx().sm_count * per_sm;
-    return (int)std::max<unsigned long long>(1, std::min(want, cap));
-}
+static unsigned fill_grid(unsigned long long nf) { return (unsigned)std::max<unsigned long long>(1, (nf / 4 + 511) / 512); }
 
 extern "C" int pbrt_texture_constant_eval_f32(float value, uint64_t n, float *out, int dst_is_device) {
     PB_API_LOCK;
@@ -1529,8 +1558,8 @@ extern "C" int pbrt_texture_constant_eval_f32(float value, uint64_t n, float *ou
     void *d_out = out;
     if (!dst_is_device)
         if (int rc = pb::out_stage(n * sizeof(float), &d_out)) return rc;
-    fill_f32_kernel<<<fill_grid(n / 4), 256, 0, ctx().stream>>>((float *)d_out, n, value);
-    PB_LAUNCH_CHECK("fill_f32_kernel");
+    fill_kernel<false><<<fill_grid(n), 128, 0, ctx().stream>>>((float *)d_out, n, value, value, value);
+    PB_LAUNCH_CHECK("fill_kernel<f32>");
     if (!dst_is_device) {
         PB_CUDA(cudaMemcpyAsync(out, d_out, n * sizeof(float), cudaMemcpyDeviceToHost, ctx().stream));
         PB_CUDA(cudaStreamSynchronize(ctx().stream));
@@ -1546,9 +1575,8 @@ extern "C" int pbrt_texture_constant_eval_rgb(const float value[3], uint64_t n, 
     void *d_out = out;
     if (!dst_is_device)
         if (int rc = pb::out_stage(n * 3 * sizeof(float), &d_out)) return rc;
-    const int blocks3 = (fill_grid(n * 3 / 4) + 2) / 3 * 3;  // thread count divisible by 3: see the kernel
-    fill_rgb_kernel<<<blocks3, 256, 0, ctx().stream>>>((float *)d_out, n, value[0], value[1], value[2]);
-    PB_LAUNCH_CHECK("fill_rgb_kernel");
+    fill_kernel<true><<<fill_grid(n * 3), 128, 0, ctx().stream>>>((float *)d_out, n * 3, value[0], value[1], value[2]);
+    PB_LAUNCH_CHECK("fill_kernel<rgb>");
     if (!dst_is_device) {
         PB_CUDA(cudaMemcpyAsync(out, d_out, n * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx().stream));
         PB_CUDA(cudaStreamSynchronize(ctx().stream));

@@ -108,6 +108,9 @@ __global__ void __launch_bounds__(256) splat_gather_generic_kernel(SplatParams P
                 aw += w;
             }
         }
+    // non-finite radiance (a contract violation) shows in the sums: 0 * x is NaN for x = inf or NaN
+    const float z = ar * 0.f + ag * 0.f + ab * 0.f + aw * 0.f;
+    if (z != z) atomicOr(P.err, ERRBIT_NONFINITE);
     flush_pixel(P.film, P.owned, x, y, ar, ag, ab, aw);
 }
 
@@ -473,6 +476,8 @@ __global__ void __launch_bounds__(256) splat_atomic_kernel(SplatParams P, int hx
             const int p1x = min(min(__float2int_rd(dx + P.rx) + 1, P.tb.x1), ox + tw);
             const int p1y = min(min(__float2int_rd(dy + P.ry) + 1, P.tb.y1), oy + th);
             const float cr = L.x * L.w, cg = L.y * L.w, cb = L.z * L.w;
+            const float z = cr * 0.f + cg * 0.f + cb * 0.f;
+            if (z != z) atomicOr(P.err, ERRBIT_NONFINITE);
             for (int y = p0y; y < p1y; ++y) {
                 const int iy = table_index(((float)y - dy) * P.iry * 16.f);
                 for (int x = p0x; x < p1x; ++x) {
