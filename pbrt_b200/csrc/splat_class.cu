@@ -284,8 +284,46 @@ __device__ __forceinline__ int class_table_index(float v) {
 // (b*w, w) addend pair costs a MOV per tap since w arrives in a register of its own; 1: (r,g) packed, b and w scalar;
 // 2: four scalars.  The fused variant (PBRT_SPLAT_FMA) always uses 2.  Indices are compile-time after unrolling.
 #ifndef PBRT_CLASS_ACC
-#define PBRT_CLASS_ACC 0
+#define PBRT_CLASS_ACC 3
 #endif
+// packed add on two scalar accumulators that the register allocator is asked to keep as an aligned pair
+__device__ __forceinline__ void cadd2s(float &a0, float &a1, float b0, float b1) {
+    asm("{\n\t.reg .b64 pa, pb;\n\tmov.b64 pa, {%0, %1};\n\tmov.b64 pb, {%2, %3};\n\tadd.rn.f32x2 pa, pa, pb;\n\tmov.b64 {%0, %1}, pa;\n\t}"
+        : "+f"(a0), "+f"(a1) : "f"(b0), "f"(b1));
+}
+template <int ROWS, int LAYOUT>
+struct ClassAcc;
+template <int ROWS>
+struct ClassAcc<ROWS, 3> {
+    float r[ROWS], g[ROWS], b[ROWS], w[ROWS];
+    __device__ __forceinline__ void clear(const int j) { r[j] = g[j] = b[j] = w[j] = 0.f; }
+    __device__ __forceinline__ void move(const int to, const int from) { r[to] = r[from]; g[to] = g[from]; b[to] = b[from]; w[to] = w[from]; }
+    __device__ __forceinline__ void get(const int j, float &R, float &G, float &B, float &Wt) const { R = r[j]; G = g[j]; B = b[j]; Wt = w[j]; }
+    __device__ __forceinline__ void tap(const int j, const float cr, const float cg, const float cb, const float wt) {
+        cadd2s(r[j], g[j], cr * wt, cg * wt);
+        cadd2s(b[j], w[j], cb * wt, wt);
+    }
+    __device__ __forceinline__ void tap_fma(const int j, const float cr, const float cg, const float cb, const float wt) {
+        r[j] = __fmaf_rn(cr, wt, r[j]); g[j] = __fmaf_rn(cg, wt, g[j]); b[j] = __fmaf_rn(cb, wt, b[j]);
+        w[j] += wt;
+    }
+};
+template <int ROWS>
+struct ClassAcc<ROWS, 4> {  // (r, g) packed, b and weight scalar
+    float r[ROWS], g[ROWS], b[ROWS], w[ROWS];
+    __device__ __forceinline__ void clear(const int j) { r[j] = g[j] = b[j] = w[j] = 0.f; }
+    __device__ __forceinline__ void move(const int to, const int from) { r[to] = r[from]; g[to] = g[from]; b[to] = b[from]; w[to] = w[from]; }
+    __device__ __forceinline__ void get(const int j, float &R, float &G, float &B, float &Wt) const { R = r[j]; G = g[j]; B = b[j]; Wt = w[j]; }
+    __device__ __forceinline__ void tap(const int j, const float cr, const float cg, const float cb, const float wt) {
+        cadd2s(r[j], g[j], cr * wt, cg * wt);
+        b[j] += cb * wt;
+        w[j] += wt;
+    }
+    __device__ __forceinline__ void tap_fma(const int j, const float cr, const float cg, const float cb, const float wt) {
+        r[j] = __fmaf_rn(cr, wt, r[j]); g[j] = __fmaf_rn(cg, wt, g[j]); b[j] = __fmaf_rn(cb, wt, b[j]);
+        w[j] += wt;
+    }
+};
 template <int ROWS, int LAYOUT>
 struct ClassAcc {
     u64 rg[LAYOUT <= 1 ? ROWS : 1];
@@ -414,6 +452,25 @@ __global__ void __launch_bounds__(TW, PBRT_CLASS_RESIDENT_THREADS / TW) splat_cl
     // are then reduced in registers; otherwise (and above 32 spp) every sample takes the general body
     const bool mask_mode = dr == 0 && spp <= 32;
     const unsigned sppmask = spp >= 32 ? 0xffffffffu : ((1u << spp) - 1u);
+    constexpr int U = PBRT_CLASS_PREPASS_BATCH;
+    // Which of this thread's batches need more than the plain classification.  The pixels of batch k are the same in
+    // every row, so both are found once, bit k per batch:
+    //   near_x:  a nominal pixel n < 3 — a phase finer than 2^-22 near the origin, p - 0.5 rounded at negative
+    //            coordinates: the careful classification;
+    //   check_x: a power of two in (n, n + H] — there floor(pd + r) can round up across the integer (see `one`):
+    //            the plain classification plus that test.
+    // Rows likewise (near_y, check_y below).  Keeping these batches cheap matters: the grid is one wave, so the
+    // strips and row segments that hold such pixels set the kernel's time.
+    unsigned near_x = 0xffffffffu, check_x = 0u;
+    if (dr == 0 && nstaged <= 32 * U * TW) {
+        near_x = 0u;
+        for (int k = 0; tid + k * U * TW < nstaged; ++k)
+            for (int u = 0; u < U; ++u) {
+                const int n = sx0 + q0 + (k * U + u) * dq;
+                if (n < 3) near_x |= 1u << k;
+                else if (__clz(n) != __clz(n + H)) check_x |= 1u << k;
+            }
+    }
 
     ClassAcc<ROWS, FMA ? 2 : PBRT_CLASS_ACC> acc;
 #pragma unroll
@@ -435,13 +492,13 @@ __global__ void __launch_bounds__(TW, PBRT_CLASS_RESIDENT_THREADS / TW) splat_cl
             const size_t row_base = ((size_t)(ny - P.sb.y0) * W + (sx0 - P.sb.x0)) * (size_t)spp;
             const float2 *gxy = P.xy + row_base;
             const float4 *grgbw = P.rgbw + row_base;
-            const float fny = (float)ny, fnyH = fny + rH;
-            const bool hazard_y = fabsf(fny) < 2.5f;
+            const float fny = (float)ny, fnyH = fny + rH, fnyh = fny + 0.5f;
+            const bool near_y = ny < 3, check_y = !near_y && __clz(ny) != __clz(ny + H);
             int sidx = r0;
             int slot = (pl_base + q0) * pitch + r0;
-            float fnx = (float)(sx0 + q0);
+            float fnxh = (float)(sx0 + q0) + 0.5f;  // nominal pixel of the thread's next sample, plus one half
             unsigned andf = 15u, orf = 0u;
-            constexpr int U = PBRT_CLASS_PREPASS_BATCH;
+            unsigned near_bits = near_x, check_bits = check_x;
             const float2 *lxy = gxy + tid;  // this thread's next sample; the batch is lxy[0], lxy[TW], ...
             const float4 *lrgbw = grgbw + tid;
             for (int e0 = tid; e0 < nstaged; e0 += U * TW, lxy += U * TW, lrgbw += U * TW) {
@@ -475,14 +532,18 @@ __global__ void __launch_bounds__(TW, PBRT_CLASS_RESIDENT_THREADS / TW) splat_cl
                         }
                     }
                 }
-                // One sample: phase, class, record.  CAREFUL = the pixels next to the origin, whose phase can be finer
-                // than 2^-22 (bounds found on the host decide); otherwise the classes are the ideal ones.
-                auto one = [&](const int u, auto careful_tag) {
-                    constexpr bool CAREFUL = decltype(careful_tag)::value;
+                // One sample: phase, class, record.  TIER 0: the classes are the ideal ones; 1: also tests whether
+                // floor(pd + r) rounds up; 2 ("careful"): the pixels next to the origin, whose phase can be finer than
+                // 2^-22 (bounds found on the host decide), and negative coordinates.
+                auto one = [&](const int u, auto tier_tag) {
+                    constexpr int TIER = decltype(tier_tag)::value;
+                    constexpr bool CAREFUL = TIER == 2;
                     const float cr = L[u].x * L[u].w, cg = L[u].y * L[u].w, cb = L[u].z * L[u].w;
-                    const float pdx = p[u].x - 0.5f, pdy = p[u].y - 0.5f;
-                    // phase: exact (Sterbenz) for a sample inside its nominal pixel
-                    const float wx = pdx - fnx, wy = pdy - fny;
+                    // phase = pd - n with pd = p - 0.5 as the CPU path rounds it: exact (Sterbenz) for a sample inside its
+                    // nominal pixel.  For n >= 1 pd itself is exact, so the phase is p - (n + 0.5) in one subtraction.
+                    const float pdx = p[u].x - 0.5f, pdy = p[u].y - 0.5f, fnx = fnxh - 0.5f;
+                    const float wx = CAREFUL ? pdx - fnx : p[u].x - fnxh;
+                    const float wy = CAREFUL ? pdy - fny : p[u].y - fnyh;
                     // contract: the sample lies in its nominal pixel (a NaN phase reaches the slow path instead)
                     vmax = fmaxf(vmax, fmaxf(fabsf(wx), fabsf(wy)));
                     unsigned offx, offy;
@@ -513,36 +574,51 @@ __global__ void __launch_bounds__(TW, PBRT_CLASS_RESIDENT_THREADS / TW) splat_cl
                         offy = classify(wy, sbase + CT_CARE_Y, CT_SLOW_Y);
                     }
                     // The classes take "pixel n + H is reached" to mean w >= 0.  The CPU path asks whether
-                    // n + H <= floor(pd + r) in floats, and pd + r can round up to the integer when it crosses a
-                    // power of two: such a sample is none of the classes.  (ceil(pd - r) has no such case: the
-                    // difference is exact wherever the result is a pixel coordinate >= 0.)
+                    // n + H <= floor(pd + r) in floats, and pd + r can round up to the integer when the sum crosses a
+                    // power of two: such a sample is none of the classes.  Only pixels with a power of two in
+                    // (n, n + H] can do that (elsewhere pd + r is exact): tiers 1 and 2.  (ceil(pd - r) has no such
+                    // case: the difference is exact wherever the result is a pixel coordinate >= 0.)
                     const unsigned sum = offx + offy;
-                    const bool ok = sum < CT_SLOW_X && !(wx < 0.f && fnx + rH <= pdx + rH) && !(wy < 0.f && fnyH <= pdy + rH);
+                    bool ok = sum < CT_SLOW_X;
+                    if (TIER >= 1) ok = ok && !(wx < 0.f && fnx + rH <= pdx + rH) && !(wy < 0.f && fnyH <= pdy + rH);
                     const unsigned fl = ok ? (sum & 15u) : CF_SLOW;
                     sts_rec(a_rec + 16u * (unsigned)slot, cr, cg, cb, sum & ~15u);
                     sts_flag(a_flag + (unsigned)slot, fl);
                     andf &= fl;
                     orf |= fl;
                 };
-                // pixels this batch touches: fnx .. fnx + (U - 1) * (dq + 1) at most
-                const bool careful = hazard_y || (fnx < 2.5f && fnx + (float)((U - 1) * (dq + 1)) > -2.5f);
-                if (full && dr == 0 && !careful) {
+                typedef std::integral_constant<int, 0> T_PLAIN;
+                typedef std::integral_constant<int, 1> T_CHECK;
+                typedef std::integral_constant<int, 2> T_CAREFUL;
+                const bool careful = near_y || (near_bits & 1u) || dr != 0;
+                const bool check = check_y || (check_bits & 1u);
+                near_bits >>= 1;
+                check_bits >>= 1;
+                if (careful) {
+                    // pixels next to the origin, or spp not dividing the strip width: bounds-checked, with the careful
+                    // classification (valid for every phase, a dozen instructions longer)
 #pragma unroll
                     for (int u = 0; u < U; ++u) {
-                        one(u, std::false_type{});
+                        if (e0 + u * TW < nstaged) one(u, T_CAREFUL{});
                         slot += slot_step;
-                        fnx += fdq;
+                        fnxh += fdq;
+                        sidx += dr;
+                        if (sidx >= spp) { sidx -= spp; slot += pitch - spp; fnxh += 1.f; }
+                    }
+                } else if (full && !check) {
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        one(u, T_PLAIN{});
+                        slot += slot_step;
+                        fnxh += fdq;
                     }
                 } else {
-                    // tail of the row, pixels next to the origin, or spp not dividing the strip width: bounds-checked,
-                    // with the careful classification (valid for every phase, a dozen instructions longer)
+                    // a pixel below a power of two, or the tail of the row (bounds-checked)
 #pragma unroll
                     for (int u = 0; u < U; ++u) {
-                        if (e0 + u * TW < nstaged) one(u, std::true_type{});
+                        if (full || e0 + u * TW < nstaged) one(u, T_CHECK{});
                         slot += slot_step;
-                        fnx += fdq;
-                        sidx += dr;
-                        if (sidx >= spp) { sidx -= spp; slot += pitch - spp; fnx += 1.f; }
+                        fnxh += fdq;
                     }
                 }
             }
@@ -608,9 +684,16 @@ __global__ void __launch_bounds__(TW, PBRT_CLASS_RESIDENT_THREADS / TW) splat_cl
                         constexpr int I0 = decltype(i0_tag)::value, I1 = decltype(i1_tag)::value;
                         const unsigned waddr = qcol + __float_as_uint(a.w);
                         float w[LIVE];
+                        if (!FMA) {
+                            // one 4-byte load per weight: each lands next to its b * w product (the (b * w, w) addend pair)
+                            // without a copy — a 16-byte load pins four weights to one aligned quad and costs a MOV each
 #pragma unroll
-                        for (int k4 = 0; k4 < LIVE / 4; ++k4)
-                            lds_blob4(waddr + 16 * k4, w[4 * k4], w[4 * k4 + 1], w[4 * k4 + 2], w[4 * k4 + 3]);
+                            for (int k = 0; k < LIVE; ++k) w[k] = lds_blob1(waddr + 4 * k);
+                        } else {
+#pragma unroll
+                            for (int k4 = 0; k4 < LIVE / 4; ++k4)
+                                lds_blob4(waddr + 16 * k4, w[4 * k4], w[4 * k4 + 1], w[4 * k4 + 2], w[4 * k4 + 3]);
+                        }
 #pragma unroll
                         for (int i = I0; i < I1; ++i) {
                             if (DOWN) tap(i + 1, a.x, a.y, a.z, w[LIVE - 1 - i]);
@@ -775,6 +858,9 @@ static int launch_class(const ClassParams &CP0) {
 
 template <int H, bool FMA>
 static int class_pick_width(const ClassParams &CP) {
+#ifdef PBRT_CLASS_PROBE  // SASS probes: one instantiation only
+    return launch_class<H, 128, FMA>(CP);
+#else
     const int force = class_env_int("PBRT_B200_TW", 0);
     if (force == 128) return launch_class<H, 128, FMA>(CP);
     if (force == 96) return launch_class<H, 96, FMA>(CP);
@@ -784,6 +870,7 @@ static int class_pick_width(const ClassParams &CP) {
     if (ClassSmem<H, 128>::bytes(CP.blob_bytes, spp) * 2 <= 226 * 1024) return launch_class<H, 128, FMA>(CP);
     if (ClassSmem<H, 64>::bytes(CP.blob_bytes, spp) * 2 <= 226 * 1024) return launch_class<H, 64, FMA>(CP);
     return launch_class<H, 32, FMA>(CP);
+#endif
 }
 
 int launch_splat_class(PbrtFilm *f, const SplatParams &P, int mode) {
@@ -800,8 +887,13 @@ int launch_splat_class(PbrtFilm *f, const SplatParams &P, int mode) {
     CP.rowp = g.ROWP;
     CP.eoff = g.EOFF;
     const bool fma = mode == PBRT_SPLAT_FMA;
+#ifdef PBRT_CLASS_PROBE
+    (void)fma;
+    return class_pick_width<PBRT_CLASS_PROBE, false>(CP);
+#else
     if (g.H == 2) return fma ? class_pick_width<2, true>(CP) : class_pick_width<2, false>(CP);
     return fma ? class_pick_width<4, true>(CP) : class_pick_width<4, false>(CP);
+#endif
 }
 
 }  // namespace pb
