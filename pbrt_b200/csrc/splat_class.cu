@@ -486,6 +486,11 @@ __global__ void __launch_bounds__(TW, PBRT_CLASS_RESIDENT_THREADS / TW) splat_cl
 
     for (int ny = cy0 - H; ny < cy1 + H; ++ny) {
         const bool row_has_samples = ny >= P.sb.y0 && ny < P.sb.y1 && nstaged > 0;
+        // the film pixel this row's flush adds to: loaded ahead of the gather, which hides the latency
+        const int yo = ny - H;
+        const bool flush = col_ok && yo >= cy0 && yo < cy1;
+        const size_t fo = (size_t)(yo - P.owned.y0) * (P.owned.x1 - P.owned.x0) + (x - P.owned.x0);
+        float4 px = make_float4(0.f, 0.f, 0.f, 0.f);
         if (row_has_samples) {
             __syncthreads();  // previous row fully consumed
             // ---------------- pre-pass: one thread per sample of the row ----------------
@@ -499,6 +504,72 @@ __global__ void __launch_bounds__(TW, PBRT_CLASS_RESIDENT_THREADS / TW) splat_cl
             float fnxh = (float)(sx0 + q0) + 0.5f;  // nominal pixel of the thread's next sample, plus one half
             unsigned andf = 15u, orf = 0u;
             unsigned near_bits = near_x, check_bits = check_x;
+            // max_sample_luminance: off (infinite) in every BASELINE config
+            auto clamp_lum = [&](float4 &Lv) {
+                const float ly = luminance(Lv.x, Lv.y, Lv.z);
+                if (ly > P.max_lum) {
+                    const float sc = P.max_lum / ly;
+                    Lv.x *= sc; Lv.y *= sc; Lv.z *= sc;
+                }
+            };
+            // One sample: phase, class, record.  TIER 0: the classes are the ideal ones; 1: also tests whether
+            // floor(pd + r) rounds up; 2 ("careful"): the pixels next to the origin, whose phase can be finer than
+            // 2^-22 (bounds found on the host decide), and negative coordinates.
+            auto one = [&](const float2 pv, const float4 Lv, const int slot_, const float fnxh_, auto tier_tag) {
+                constexpr int TIER = decltype(tier_tag)::value;
+                constexpr bool CAREFUL = TIER == 2;
+                const float cr = Lv.x * Lv.w, cg = Lv.y * Lv.w, cb = Lv.z * Lv.w;
+                // phase = pd - n with pd = p - 0.5 as the CPU path rounds it: exact (Sterbenz) for a sample inside its
+                // nominal pixel.  For n >= 1 pd itself is exact, so the phase is p - (n + 0.5) in one subtraction.
+                const float pdx = pv.x - 0.5f, pdy = pv.y - 0.5f, fnx = fnxh_ - 0.5f;
+                const float wx = CAREFUL ? pdx - fnx : pv.x - fnxh_;
+                const float wy = CAREFUL ? pdy - fny : pv.y - fnyh;
+                // contract: the sample lies in its nominal pixel (a NaN phase reaches the slow path instead)
+                vmax = fmaxf(vmax, fmaxf(fabsf(wx), fabsf(wy)));
+                unsigned offx, offy;
+                if (!CAREFUL) {
+                    auto classify = [&](const float w, const unsigned lut) {
+                        float t = __fmaf_rn(w, (float)K, 0.5f * (float)K);
+                        t = fminf(fabsf(t), (float)(CT_LUT_ENTRIES - 1));
+                        const unsigned cell = (unsigned)__float_as_int(__fadd_rd(t, 8388608.f));
+                        float point, oi, op, pad;
+                        lds_blob4(__dp4a(cell, 16u, lut), point, oi, op, pad);
+                        return __float_as_uint(w == point ? op : oi);
+                    };
+                    offx = classify(wx, sbase + CT_LUT_X);
+                    offy = classify(wy, sbase + CT_LUT_Y);
+                } else {
+                    auto classify = [&](const float w, const unsigned lut, const unsigned slow) {
+                        float t = __fmaf_rn(w, (float)K, 0.5f * (float)K + 0.5f);
+                        t = fminf(fabsf(t), (float)(CT_CARE_ENTRIES - 1));
+                        const unsigned cell = (unsigned)__float_as_int(__fadd_rd(t, 8388608.f));
+                        const unsigned e = __dp4a(cell, 32u, lut);
+                        float glo, ghi, point, pad0, ob, op, oa, pad1;
+                        lds_blob4(e, glo, ghi, point, pad0);
+                        lds_blob4(e + 16, ob, op, oa, pad1);
+                        return w < glo ? __float_as_uint(ob)
+                                       : (w > ghi ? __float_as_uint(oa) : (w == point ? __float_as_uint(op) : slow));
+                    };
+                    offx = classify(wx, sbase + CT_CARE_X, CT_SLOW_X);
+                    offy = classify(wy, sbase + CT_CARE_Y, CT_SLOW_Y);
+                }
+                // The classes take "pixel n + H is reached" to mean w >= 0.  The CPU path asks whether
+                // n + H <= floor(pd + r) in floats, and pd + r can round up to the integer when the sum crosses a
+                // power of two: such a sample is none of the classes.  Only pixels with a power of two in
+                // (n, n + H] can do that (elsewhere pd + r is exact): tiers 1 and 2.  (ceil(pd - r) has no such
+                // case: the difference is exact wherever the result is a pixel coordinate >= 0.)
+                const unsigned sum = offx + offy;
+                bool ok = sum < CT_SLOW_X;
+                if (TIER >= 1) ok = ok && !(wx < 0.f && fnx + rH <= pdx + rH) && !(wy < 0.f && fnyH <= pdy + rH);
+                const unsigned fl = ok ? (sum & 15u) : CF_SLOW;
+                sts_rec(a_rec + 16u * (unsigned)slot_, cr, cg, cb, sum & ~15u);
+                sts_flag(a_flag + (unsigned)slot_, fl);
+                andf &= fl;
+                orf |= fl;
+            };
+            typedef std::integral_constant<int, 0> T_PLAIN;
+            typedef std::integral_constant<int, 1> T_CHECK;
+            typedef std::integral_constant<int, 2> T_CAREFUL;
             const float2 *lxy = gxy + tid;  // this thread's next sample; the batch is lxy[0], lxy[TW], ...
             const float4 *lrgbw = grgbw + tid;
             for (int e0 = tid; e0 < nstaged; e0 += U * TW, lxy += U * TW, lrgbw += U * TW) {
@@ -520,76 +591,11 @@ __global__ void __launch_bounds__(TW, PBRT_CLASS_RESIDENT_THREADS / TW) splat_cl
                         }
                     }
                 }
-                if (clamp_on) {  // max_sample_luminance, off (infinite) in every BASELINE config: kept out of the main body
+                if (clamp_on) {
 #pragma unroll
-                    for (int u = 0; u < U; ++u) {
-                        if (full || e0 + u * TW < nstaged) {
-                            const float ly = luminance(L[u].x, L[u].y, L[u].z);
-                            if (ly > P.max_lum) {
-                                const float sc = P.max_lum / ly;
-                                L[u].x *= sc; L[u].y *= sc; L[u].z *= sc;
-                            }
-                        }
-                    }
+                    for (int u = 0; u < U; ++u)
+                        if (full || e0 + u * TW < nstaged) clamp_lum(L[u]);
                 }
-                // One sample: phase, class, record.  TIER 0: the classes are the ideal ones; 1: also tests whether
-                // floor(pd + r) rounds up; 2 ("careful"): the pixels next to the origin, whose phase can be finer than
-                // 2^-22 (bounds found on the host decide), and negative coordinates.
-                auto one = [&](const int u, auto tier_tag) {
-                    constexpr int TIER = decltype(tier_tag)::value;
-                    constexpr bool CAREFUL = TIER == 2;
-                    const float cr = L[u].x * L[u].w, cg = L[u].y * L[u].w, cb = L[u].z * L[u].w;
-                    // phase = pd - n with pd = p - 0.5 as the CPU path rounds it: exact (Sterbenz) for a sample inside its
-                    // nominal pixel.  For n >= 1 pd itself is exact, so the phase is p - (n + 0.5) in one subtraction.
-                    const float pdx = p[u].x - 0.5f, pdy = p[u].y - 0.5f, fnx = fnxh - 0.5f;
-                    const float wx = CAREFUL ? pdx - fnx : p[u].x - fnxh;
-                    const float wy = CAREFUL ? pdy - fny : p[u].y - fnyh;
-                    // contract: the sample lies in its nominal pixel (a NaN phase reaches the slow path instead)
-                    vmax = fmaxf(vmax, fmaxf(fabsf(wx), fabsf(wy)));
-                    unsigned offx, offy;
-                    if (!CAREFUL) {
-                        auto classify = [&](const float w, const unsigned lut) {
-                            float t = __fmaf_rn(w, (float)K, 0.5f * (float)K);
-                            t = fminf(fabsf(t), (float)(CT_LUT_ENTRIES - 1));
-                            const unsigned cell = (unsigned)__float_as_int(__fadd_rd(t, 8388608.f));
-                            float point, oi, op, pad;
-                            lds_blob4(__dp4a(cell, 16u, lut), point, oi, op, pad);
-                            return __float_as_uint(w == point ? op : oi);
-                        };
-                        offx = classify(wx, sbase + CT_LUT_X);
-                        offy = classify(wy, sbase + CT_LUT_Y);
-                    } else {
-                        auto classify = [&](const float w, const unsigned lut, const unsigned slow) {
-                            float t = __fmaf_rn(w, (float)K, 0.5f * (float)K + 0.5f);
-                            t = fminf(fabsf(t), (float)(CT_CARE_ENTRIES - 1));
-                            const unsigned cell = (unsigned)__float_as_int(__fadd_rd(t, 8388608.f));
-                            const unsigned e = __dp4a(cell, 32u, lut);
-                            float glo, ghi, point, pad0, ob, op, oa, pad1;
-                            lds_blob4(e, glo, ghi, point, pad0);
-                            lds_blob4(e + 16, ob, op, oa, pad1);
-                            return w < glo ? __float_as_uint(ob)
-                                           : (w > ghi ? __float_as_uint(oa) : (w == point ? __float_as_uint(op) : slow));
-                        };
-                        offx = classify(wx, sbase + CT_CARE_X, CT_SLOW_X);
-                        offy = classify(wy, sbase + CT_CARE_Y, CT_SLOW_Y);
-                    }
-                    // The classes take "pixel n + H is reached" to mean w >= 0.  The CPU path asks whether
-                    // n + H <= floor(pd + r) in floats, and pd + r can round up to the integer when the sum crosses a
-                    // power of two: such a sample is none of the classes.  Only pixels with a power of two in
-                    // (n, n + H] can do that (elsewhere pd + r is exact): tiers 1 and 2.  (ceil(pd - r) has no such
-                    // case: the difference is exact wherever the result is a pixel coordinate >= 0.)
-                    const unsigned sum = offx + offy;
-                    bool ok = sum < CT_SLOW_X;
-                    if (TIER >= 1) ok = ok && !(wx < 0.f && fnx + rH <= pdx + rH) && !(wy < 0.f && fnyH <= pdy + rH);
-                    const unsigned fl = ok ? (sum & 15u) : CF_SLOW;
-                    sts_rec(a_rec + 16u * (unsigned)slot, cr, cg, cb, sum & ~15u);
-                    sts_flag(a_flag + (unsigned)slot, fl);
-                    andf &= fl;
-                    orf |= fl;
-                };
-                typedef std::integral_constant<int, 0> T_PLAIN;
-                typedef std::integral_constant<int, 1> T_CHECK;
-                typedef std::integral_constant<int, 2> T_CAREFUL;
                 const bool careful = near_y || (near_bits & 1u) || dr != 0;
                 const bool check = check_y || (check_bits & 1u);
                 near_bits >>= 1;
@@ -599,7 +605,7 @@ __global__ void __launch_bounds__(TW, PBRT_CLASS_RESIDENT_THREADS / TW) splat_cl
                     // classification (valid for every phase, a dozen instructions longer)
 #pragma unroll
                     for (int u = 0; u < U; ++u) {
-                        if (e0 + u * TW < nstaged) one(u, T_CAREFUL{});
+                        if (e0 + u * TW < nstaged) one(p[u], L[u], slot, fnxh, T_CAREFUL{});
                         slot += slot_step;
                         fnxh += fdq;
                         sidx += dr;
@@ -608,7 +614,7 @@ __global__ void __launch_bounds__(TW, PBRT_CLASS_RESIDENT_THREADS / TW) splat_cl
                 } else if (full && !check) {
 #pragma unroll
                     for (int u = 0; u < U; ++u) {
-                        one(u, T_PLAIN{});
+                        one(p[u], L[u], slot, fnxh, T_PLAIN{});
                         slot += slot_step;
                         fnxh += fdq;
                     }
@@ -616,7 +622,7 @@ __global__ void __launch_bounds__(TW, PBRT_CLASS_RESIDENT_THREADS / TW) splat_cl
                     // a pixel below a power of two, or the tail of the row (bounds-checked)
 #pragma unroll
                     for (int u = 0; u < U; ++u) {
-                        if (full || e0 + u * TW < nstaged) one(u, T_CHECK{});
+                        if (full || e0 + u * TW < nstaged) one(p[u], L[u], slot, fnxh, T_CHECK{});
                         slot += slot_step;
                         fnxh += fdq;
                     }
@@ -647,6 +653,7 @@ __global__ void __launch_bounds__(TW, PBRT_CLASS_RESIDENT_THREADS / TW) splat_cl
                 asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(nrgbw), "r"((unsigned)(nstaged * 16)) : "memory");
             }
 #endif
+            if (flush) px = P.film[fo];
             // ---------------- gather: this thread's column against the row ----------------
             if (col_ok) {
                 const unsigned m_up = mask_mode ? ~mk[0] & sppmask : 0u, m_down = mask_mode ? ~mk[1] & sppmask : 0u;
@@ -798,15 +805,13 @@ __global__ void __launch_bounds__(TW, PBRT_CLASS_RESIDENT_THREADS / TW) splat_cl
             parity ^= 1;
         }
         // output row ny - H is complete: no later sample row reaches it
-        const int yo = ny - H;
-        if (col_ok && yo >= cy0 && yo < cy1) {
+        if (flush) {
             float r, g, b, w;
             acc.get(0, r, g, b, w);
             // non-finite radiance (a contract violation) shows in the sums: 0 * x is NaN for x = inf or NaN
             const float z = r * 0.f + g * 0.f + b * 0.f + w * 0.f;
             if (z != z) errbits |= ERRBIT_NONFINITE;
-            const size_t fo = (size_t)(yo - P.owned.y0) * (P.owned.x1 - P.owned.x0) + (x - P.owned.x0);
-            float4 px = P.film[fo];
+            if (!row_has_samples) px = P.film[fo];
             float X, Y, Z;
             rgb_to_xyz(r, g, b, X, Y, Z);
             px.x += X; px.y += Y; px.z += Z; px.w += w;
