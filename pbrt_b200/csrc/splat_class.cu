@@ -243,6 +243,10 @@ struct ClassParams {
     int blob_bytes;
     int rowp;
     int eoff;
+    const int *seg_start;  // first output row of each row segment (blockIdx.y), one past the last at [gridDim.y]
+#ifdef PBRT_CLASS_TRACE
+    unsigned long long *trace;  // per CTA {smid, start ns, end ns, rows} (tools/cta_trace.py)
+#endif
 };
 
 __device__ __forceinline__ u64 cpack2(float lo, float hi) {
@@ -413,6 +417,10 @@ __global__ void __launch_bounds__(TW, PBRT_CLASS_RESIDENT_THREADS / TW) splat_cl
     const SplatParams &P = CP.S;
     extern __shared__ __align__(16) unsigned char smem[];
     const int tid = threadIdx.x;
+#ifdef PBRT_CLASS_TRACE
+    unsigned long long trace_t0 = 0;
+    if (tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(trace_t0));
+#endif
     const int spp = P.spp;
     const int pitch = ClassSmem<H, TW>::pitch(spp);
     unsigned *s_mask = reinterpret_cast<unsigned *>(smem + CP.blob_bytes);
@@ -429,8 +437,8 @@ __global__ void __launch_bounds__(TW, PBRT_CLASS_RESIDENT_THREADS / TW) splat_cl
     const unsigned a_flag = a_rec + (unsigned)(NPX * pitch) * 16u;
 
     const int cx0 = P.tb.x0 + blockIdx.x * TW;              // first output column of the strip
-    const int cy0 = P.tb.y0 + blockIdx.y * P.rows_per_cta;  // first output row
-    const int cy1 = min(cy0 + P.rows_per_cta, P.tb.y1);
+    const int cy0 = CP.seg_start[blockIdx.y];  // first output row
+    const int cy1 = CP.seg_start[blockIdx.y + 1];
     const int x = cx0 + tid;
     const bool col_ok = x < P.tb.x1;
     const float fx = (float)x;
@@ -823,6 +831,17 @@ __global__ void __launch_bounds__(TW, PBRT_CLASS_RESIDENT_THREADS / TW) splat_cl
     }
     if (!(vmax <= 0.5f)) errbits |= ERRBIT_NOT_PIXEL_MAJOR;
     if (errbits) atomicOr(P.err, (int)errbits);
+#ifdef PBRT_CLASS_TRACE
+    __syncthreads();
+    if (tid == 0 && CP.trace) {
+        unsigned long long t1;
+        unsigned smid;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        unsigned long long *t = CP.trace + 4 * (size_t)(blockIdx.y * gridDim.x + blockIdx.x);
+        t[0] = smid; t[1] = trace_t0; t[2] = t1; t[3] = (unsigned long long)(cy1 - cy0);
+    }
+#endif
 }
 
 // ---- launch ------------------------------------------------------------------------------------------------------
@@ -830,6 +849,74 @@ __global__ void __launch_bounds__(TW, PBRT_CLASS_RESIDENT_THREADS / TW) splat_cl
 static int class_env_int(const char *name, int dflt) {
     const char *v = getenv(name);
     return v && *v ? atoi(v) : dflt;
+}
+
+#ifdef PBRT_CLASS_TRACE
+static unsigned long long *g_trace = nullptr;
+static int g_trace_n = 0, g_trace_cols = 0;
+#endif
+
+// Row segments of the one-wave grid.  The CTAs resident on an SM do not run at the same pace: the warp scheduler favours
+// the older ones, so with equal segments the first CTA of an SM finishes ~15 % ahead of the fourth and its slot then
+// idles to the end of the kernel (per-CTA trace: tools/cta_trace.py, profiles/r2_cta_trace.txt).  CTAs are placed
+// round-robin by linear block id, so the residency rank of a segment's CTAs is (blockIdx.y * cols + x) / SMs; segments
+// of a slower rank get fewer rows: rows + c = T * w[rank], c = the cost of the 2h halo sample rows in row units.
+static cudaError_t class_segments(int y0, int rows, int cols, int segs, int per_sm, int H, const int **d_out) {
+    static int *d_seg = nullptr;
+    static int cap = 0;
+    static std::vector<int> host;
+    static int key[7] = {-1, -1, -1, -1, -1, -1, -1};
+    static double w[8] = {1.0, 0.95, 0.90, 0.865, 0.83, 0.80, 0.77, 0.74};
+    static double halo_c = -1.0;
+    if (halo_c < 0.0) {
+        halo_c = 1.2;
+        if (const char *v = getenv("PBRT_B200_HALO_C")) halo_c = atof(v);
+        if (const char *v = getenv("PBRT_B200_RANK_W")) {
+            int i = 0;
+            for (const char *q = v; *q && i < 8; ++i) {
+                w[i] = atof(q);
+                while (*q && *q != ',') ++q;
+                if (*q == ',') ++q;
+            }
+            for (; i < 8 && i > 0; ++i) w[i] = w[i - 1];
+        }
+    }
+    const int k[7] = {y0, rows, cols, segs, per_sm, H, ctx().device};
+    if (memcmp(k, key, sizeof k) != 0 || !d_seg) {
+        if (segs + 1 > cap) {
+            if (d_seg) cudaFree(d_seg);
+            d_seg = nullptr;
+            cap = 0;
+            cudaError_t e = cudaMalloc(&d_seg, (size_t)(segs + 1 + 64) * sizeof(int));
+            if (e != cudaSuccess) return e;
+            cap = segs + 1 + 64;
+        }
+        const int nsm = ctx().sm_count;
+        std::vector<double> ws(segs);
+        double wsum = 0.0;
+        for (int s = 0; s < segs; ++s) {
+            const int rank = std::min(std::min(per_sm, 8) - 1, (s * cols + cols / 2) / nsm);
+            ws[s] = w[rank];
+            wsum += ws[s];
+        }
+        const double c = halo_c * H, T = (rows + segs * c) / wsum;
+        host.assign(segs + 1, 0);
+        double acc = 0.0;
+        for (int s = 0; s < segs; ++s) {
+            host[s] = (int)(acc + 0.5);
+            acc += std::max(1.0, T * ws[s] - c);
+        }
+        host[segs] = rows;
+        // every segment keeps at least one row (segs <= rows)
+        for (int s = 1; s < segs; ++s) host[s] = std::max(host[s], host[s - 1] + 1);
+        for (int s = segs - 1; s > 0; --s) host[s] = std::min(host[s], host[s + 1] - 1);
+        for (int s = 0; s <= segs; ++s) host[s] += y0;
+        cudaError_t e = cudaMemcpyAsync(d_seg, host.data(), (size_t)(segs + 1) * sizeof(int), cudaMemcpyHostToDevice, ctx().stream);
+        if (e != cudaSuccess) return e;
+        memcpy(key, k, sizeof k);
+    }
+    *d_out = d_seg;
+    return cudaSuccess;
 }
 
 template <int H, int TW, bool FMA>
@@ -853,9 +940,16 @@ static int launch_class(const ClassParams &CP0) {
     int segs = std::max(1, resident / cols);
     segs = std::min(segs, std::max(1, rows / (4 * H)));
     const int rpc = class_env_int("PBRT_B200_ROWS_PER_CTA", 0);
-    P.rows_per_cta = rpc > 0 ? rpc : (rows + segs - 1) / segs;
-    segs = (rows + P.rows_per_cta - 1) / P.rows_per_cta;
+    if (rpc > 0) segs = (rows + rpc - 1) / rpc;
+    P.rows_per_cta = (rows + segs - 1) / segs;
+    PB_CUDA(class_segments(P.tb.y0, rows, cols, segs, per_sm, H, &CP.seg_start));
     dim3 grid(cols, segs);
+#ifdef PBRT_CLASS_TRACE
+    static unsigned long long *d_trace = nullptr;
+    if (!d_trace) PB_CUDA(cudaMalloc(&d_trace, 4 * sizeof(unsigned long long) * 65536));
+    CP.trace = cols * segs <= 65536 ? d_trace : nullptr;
+    g_trace = d_trace; g_trace_n = cols * segs; g_trace_cols = cols;
+#endif
     splat_class_kernel<H, TW, FMA><<<grid, TW, smem, ctx().stream>>>(CP);
     PB_LAUNCH_CHECK("splat_class_kernel");
     return PBRT_OK;
@@ -918,3 +1012,15 @@ extern "C" int pbrt_b200_debug_class_tables(const float table[256], float rx, fl
     if (out && cap > 0) memcpy(out, blob.data(), std::min<size_t>(blob.size(), (size_t)cap));
     return (int)blob.size();
 }
+
+#ifdef PBRT_CLASS_TRACE
+// [UTIL, debug builds only] the per-CTA trace of the last splat_class_kernel launch: n x {smid, start ns, end ns, rows}
+extern "C" int pbrt_b200_debug_cta_trace(unsigned long long *out, int cap, int *cols) {
+    if (!pb::g_trace) return 0;
+    cudaDeviceSynchronize();
+    const int n = pb::g_trace_n < cap ? pb::g_trace_n : cap;
+    cudaMemcpy(out, pb::g_trace, (size_t)n * 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    if (cols) *cols = pb::g_trace_cols;
+    return n;
+}
+#endif
