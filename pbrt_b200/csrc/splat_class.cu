@@ -244,6 +244,7 @@ struct ClassParams {
     int rowp;
     int eoff;
     const int *seg_start;  // first output row of each row segment (blockIdx.y), one past the last at [gridDim.y]
+    int wait_first;        // wait for the preceding grid before anything is read (see launch_class)
 #ifdef PBRT_CLASS_TRACE
     unsigned long long *trace;  // per CTA {smid, start ns, end ns, rows} (tools/cta_trace.py)
 #endif
@@ -417,6 +418,12 @@ __global__ void __launch_bounds__(TW, PBRT_CLASS_RESIDENT_THREADS / TW) splat_cl
     const SplatParams &P = CP.S;
     extern __shared__ __align__(16) unsigned char smem[];
     const int tid = threadIdx.x;
+    // Programmatic dependent launch: the next splat launch of the stream may fill the SM slots this grid's early finishers
+    // leave (the grid is one wave, its tail would idle otherwise).  Nothing a splat launch reads before its first flush
+    // is written by the splat launch ahead of it; the film is, so its first access waits for that grid (film_wait).
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    bool film_ready = false;
+    if (CP.wait_first) { asm volatile("griddepcontrol.wait;" ::: "memory"); film_ready = true; }
 #ifdef PBRT_CLASS_TRACE
     unsigned long long trace_t0 = 0;
     if (tid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(trace_t0));
@@ -613,7 +620,11 @@ __global__ void __launch_bounds__(TW, PBRT_CLASS_RESIDENT_THREADS / TW) splat_cl
                     // classification (valid for every phase, a dozen instructions longer)
 #pragma unroll
                     for (int u = 0; u < U; ++u) {
-                        if (e0 + u * TW < nstaged) one(p[u], L[u], slot, fnxh, T_CAREFUL{});
+                        if (e0 + u * TW < nstaged) {
+                            // only the samples of those pixels: the rest of the batch takes the checked plain form
+                            if (near_y || dr != 0 || fnxh < 3.f) one(p[u], L[u], slot, fnxh, T_CAREFUL{});
+                            else one(p[u], L[u], slot, fnxh, T_CHECK{});
+                        }
                         slot += slot_step;
                         fnxh += fdq;
                         sidx += dr;
@@ -661,7 +672,10 @@ __global__ void __launch_bounds__(TW, PBRT_CLASS_RESIDENT_THREADS / TW) splat_cl
                 asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(nrgbw), "r"((unsigned)(nstaged * 16)) : "memory");
             }
 #endif
-            if (flush) px = P.film[fo];
+            if (flush) {
+                if (!film_ready) { asm volatile("griddepcontrol.wait;" ::: "memory"); film_ready = true; }
+                px = P.film[fo];
+            }
             // ---------------- gather: this thread's column against the row ----------------
             if (col_ok) {
                 const unsigned m_up = mask_mode ? ~mk[0] & sppmask : 0u, m_down = mask_mode ? ~mk[1] & sppmask : 0u;
@@ -819,7 +833,10 @@ __global__ void __launch_bounds__(TW, PBRT_CLASS_RESIDENT_THREADS / TW) splat_cl
             // non-finite radiance (a contract violation) shows in the sums: 0 * x is NaN for x = inf or NaN
             const float z = r * 0.f + g * 0.f + b * 0.f + w * 0.f;
             if (z != z) errbits |= ERRBIT_NONFINITE;
-            if (!row_has_samples) px = P.film[fo];
+            if (!row_has_samples) {
+                if (!film_ready) { asm volatile("griddepcontrol.wait;" ::: "memory"); film_ready = true; }
+                px = P.film[fo];
+            }
             float X, Y, Z;
             rgb_to_xyz(r, g, b, X, Y, Z);
             px.x += X; px.y += Y; px.z += Z; px.w += w;
@@ -831,6 +848,8 @@ __global__ void __launch_bounds__(TW, PBRT_CLASS_RESIDENT_THREADS / TW) splat_cl
     }
     if (!(vmax <= 0.5f)) errbits |= ERRBIT_NOT_PIXEL_MAJOR;
     if (errbits) atomicOr(P.err, (int)errbits);
+    // a CTA that never touched the film must not let the grid complete ahead of the one before it
+    if (!film_ready) asm volatile("griddepcontrol.wait;" ::: "memory");
 #ifdef PBRT_CLASS_TRACE
     __syncthreads();
     if (tid == 0 && CP.trace) {
@@ -866,7 +885,7 @@ static cudaError_t class_segments(int y0, int rows, int cols, int segs, int per_
     static int cap = 0;
     static std::vector<int> host;
     static int key[7] = {-1, -1, -1, -1, -1, -1, -1};
-    static double w[8] = {1.0, 0.95, 0.90, 0.865, 0.83, 0.80, 0.77, 0.74};
+    static double w[8] = {1.0, 0.97, 0.93, 0.885, 0.85, 0.82, 0.79, 0.76};  // measured on C2 / C3 / C5, back-to-back launches
     static double halo_c = -1.0;
     if (halo_c < 0.0) {
         halo_c = 1.2;
@@ -950,8 +969,28 @@ static int launch_class(const ClassParams &CP0) {
     CP.trace = cols * segs <= 65536 ? d_trace : nullptr;
     g_trace = d_trace; g_trace_n = cols * segs; g_trace_cols = cols;
 #endif
-    splat_class_kernel<H, TW, FMA><<<grid, TW, smem, ctx().stream>>>(CP);
+    // The sample streams are read before the film wait.  That is safe when they were complete before the preceding grid
+    // began — taken to hold when this launch reads the very buffers the preceding splat launch read (a multi-pass
+    // render over resident samples); any other launch waits first and overlaps only its table staging.
+    static const void *last_xy = nullptr, *last_rgbw = nullptr;
+    static uint64_t last_launch = ~0ull;
+    CP.wait_first = !(last_xy == P.xy && last_rgbw == P.rgbw && last_launch == ctx().launches && !P.tiles) ||
+                    class_env_int("PBRT_B200_PDL_WAIT_FIRST", 0);
+    last_xy = P.xy;
+    last_rgbw = P.rgbw;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(TW);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = ctx().stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = class_env_int("PBRT_B200_NO_PDL", 0) ? 0 : 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    PB_CUDA(cudaLaunchKernelEx(&cfg, splat_class_kernel<H, TW, FMA>, CP));
     PB_LAUNCH_CHECK("splat_class_kernel");
+    last_launch = ctx().launches;  // the library launched nothing else since, if this still equals ctx().launches next time
     return PBRT_OK;
 }
 
