@@ -739,10 +739,18 @@ __global__ void __launch_bounds__(TW, PBRT_CLASS_RESIDENT_THREADS / TW) splat_cl
                     };
                     auto run_bits = [&](unsigned bits, auto down_tag, auto i0_tag, auto i1_tag) {
                         if (decltype(i0_tag)::value >= decltype(i1_tag)::value) return;
-                        while (bits) {
+                        while (bits) {  // two at a time where neighbours are set (stratified streams: always)
                             const int s0 = __ffs((int)bits) - 1;
-                            bits &= bits - 1;
-                            body(pa[s0], down_tag, i0_tag, i1_tag);
+                            const unsigned two = 3u << s0;
+                            if ((bits & two) == two) {
+                                const float4 a0 = pa[s0], a1 = pa[s0 + 1];
+                                bits &= ~two;
+                                body(a0, down_tag, i0_tag, i1_tag);
+                                body(a1, down_tag, i0_tag, i1_tag);
+                            } else {
+                                bits &= bits - 1;
+                                body(pa[s0], down_tag, i0_tag, i1_tag);
+                            }
                         }
                     };
                     if (simple_rows && (interior || (d == -H ? simple_right : simple_left))) {
@@ -756,15 +764,29 @@ __global__ void __launch_bounds__(TW, PBRT_CLASS_RESIDENT_THREADS / TW) splat_cl
                                 run_bits(run_down, std::true_type{}, d0, d1);
                             }
                         };
-                        typedef std::integral_constant<int, 1> I_1;
-                        typedef std::integral_constant<int, LIVE - 1> I_L1;
-                        typedef std::integral_constant<int, LIVE - 2> I_L2;
-                        typedef std::integral_constant<int, 2> I_2;
-                        if (H != 2 || band == 0 || band > 2 || band < -2) visit(I_0{}, I_LIVE{}, I_0{}, I_LIVE{});
-                        else if (band == 2) visit(I_0{}, I_0{}, I_L1{}, I_LIVE{});      // window row 4: the last tap of "down"
-                        else if (band == 1) visit(I_L1{}, I_LIVE{}, I_L2{}, I_LIVE{});  // rows 3, 4
-                        else if (band == -1) visit(I_0{}, I_2{}, I_0{}, I_1{});         // rows 0, 1
-                        else visit(I_0{}, I_1{}, I_0{}, I_0{});                         // row 0: the first tap of "up"
+                        // Halo rows: the b-th sample row above the segment reaches window rows >= H + b only — taps
+                        // [H + b, LIVE) of "up", [H + b - 1, LIVE) of "down"; the b-th below, window rows <= H - b —
+                        // taps [0, H - b + 1) of "up", [0, H - b) of "down".  One instantiation per band.
+                        auto above = [&](auto b_tag) {
+                            constexpr int B = decltype(b_tag)::value;
+                            visit(std::integral_constant<int, (H + B < LIVE ? H + B : LIVE)>{}, I_LIVE{},
+                                  std::integral_constant<int, H + B - 1>{}, I_LIVE{});
+                        };
+                        auto below = [&](auto b_tag) {
+                            constexpr int B = decltype(b_tag)::value;
+                            visit(I_0{}, std::integral_constant<int, H - B + 1>{}, I_0{}, std::integral_constant<int, H - B>{});
+                        };
+                        typedef std::integral_constant<int, 1> B_1;
+                        typedef std::integral_constant<int, 2> B_2;
+                        if (band == 0 || band > H || band < -H) visit(I_0{}, I_LIVE{}, I_0{}, I_LIVE{});
+                        else if (band == 1) above(B_1{});
+                        else if (band == 2) above(B_2{});
+                        else if (band == -1) below(B_1{});
+                        else if (band == -2) below(B_2{});
+                        else if (H == 4 && band == 3) above(std::integral_constant<int, (H == 4 ? 3 : 1)>{});
+                        else if (H == 4 && band == 4) above(std::integral_constant<int, (H == 4 ? 4 : 1)>{});
+                        else if (H == 4 && band == -3) below(std::integral_constant<int, (H == 4 ? 3 : 1)>{});
+                        else below(std::integral_constant<int, (H == 4 ? 4 : 1)>{});
                         continue;
                     }
                     // a sample of any kind, decided per lane
