@@ -55,7 +55,12 @@ constexpr int CT_Q_OFFSET = CT_CARE_X + CT_CARE_BYTES;
 constexpr unsigned CT_SLOW_X = 0x40000000u, CT_SLOW_Y = 0x80000000u;
 constexpr int CT_ZERO = 16;  // "not reached" in a profile
 // flag bits in the low nibble of a LUT offset (block addresses are multiples of 16)
-constexpr unsigned CF_DOWN = 1, CF_BOTH = 2, CF_LEFT = 4, CF_RIGHT = 8, CF_SLOW = 15;
+// CF_UP: the class can be gathered as "up" (window rows 0..2h-1 in storage order), CF_DOWN: as "down" (rows 1..2h, the
+// mirrored block in reverse).  A phase of exactly 0 reaches all 2h+1 rows and carries both: its block is its own mirror
+// image, so it runs with whichever kind its sample index has in the row and gets one more tap — on window row 2h after
+// an "up" run, on row 0 after a "down" run (CF_BOTH).  CF_SLOW carries neither: a classless sample makes its sample
+// index neither "up" nor "down" in the per-index masks.
+constexpr unsigned CF_UP = 1, CF_DOWN = 2, CF_BOTH = 3, CF_LEFT = 4, CF_RIGHT = 8, CF_SLOW = 12;
 
 template <int H> struct ClassCfg {
     static constexpr int ROWS = 2 * H + 1;
@@ -167,7 +172,7 @@ static bool class_tables_host(const float table[256], float rx, float ry, std::v
     auto offx = [&](int c) { return (uint32_t)(c * g.BLK) | (c <= K ? CF_LEFT : 0u) | (c >= K ? CF_RIGHT : 0u); };
     auto offy = [&](int c) {
         const int row = c <= K ? c : 2 * K - c;
-        return (uint32_t)(CT_Q_OFFSET + row * g.ROWP) | (c > K ? CF_DOWN : 0u) | (c == K ? CF_BOTH : 0u);
+        return (uint32_t)(CT_Q_OFFSET + row * g.ROWP) | (c <= K ? CF_UP : 0u) | (c >= K ? CF_DOWN : 0u);
     };
     struct Fast { float point; uint32_t off_interval, off_point, pad; };
     struct Care { float glo, ghi, point, pad0; uint32_t off_below, off_point, off_above, pad1; };
@@ -653,11 +658,13 @@ __global__ void __launch_bounds__(TW, PBRT_CLASS_RESIDENT_THREADS / TW) splat_cl
             }
             // per sample index: is every sample of the strip "up" / "down", does every / no sample reach the outermost
             // column on the left / right.  Words: 0 !up 1 !down 2 !left-all 3 !left-none 4 !right-all 5 !right-none
+            // 6 some sample may have phase 0 (its extra tap follows the run it is in)
             unsigned *mk = s_mask + parity * 8;
             if (mask_mode && tid < nstaged) {
                 const unsigned bit = 1u << r0;
-                if (orf & 3u) atomicOr(&mk[0], bit);
-                if (!(andf & CF_DOWN) || (orf & CF_BOTH)) atomicOr(&mk[1], bit);
+                if (!(andf & CF_UP)) atomicOr(&mk[0], bit);
+                if (!(andf & CF_DOWN)) atomicOr(&mk[1], bit);
+                if ((orf & CF_BOTH) == CF_BOTH) atomicOr(&mk[6], bit);
                 if (!(andf & CF_LEFT)) atomicOr(&mk[2], bit);
                 if (orf & CF_LEFT) atomicOr(&mk[3], bit);
                 if (!(andf & CF_RIGHT)) atomicOr(&mk[4], bit);
@@ -685,6 +692,7 @@ __global__ void __launch_bounds__(TW, PBRT_CLASS_RESIDENT_THREADS / TW) splat_cl
                 const unsigned m_up = mask_mode ? ~mk[0] & sppmask : 0u, m_down = mask_mode ? ~mk[1] & sppmask : 0u;
                 const unsigned m_lall = ~mk[2] & sppmask, m_lnone = mask_mode ? ~mk[3] & sppmask : 0u;
                 const unsigned m_rall = ~mk[4] & sppmask, m_rnone = mask_mode ? ~mk[5] & sppmask : 0u;
+                const unsigned m_both = mk[6] & sppmask;
                 // A "simple" row (every stratified row without a phase-0 or classless sample): sample indices 0..n_up-1 are
                 // "up" everywhere in the strip, the rest "down", and each index either always or never reaches an
                 // outermost column.  Its visits are two loops with no per-sample decisions.
@@ -733,6 +741,14 @@ __global__ void __launch_bounds__(TW, PBRT_CLASS_RESIDENT_THREADS / TW) splat_cl
                             else tap(i, a.x, a.y, a.z, w[i]);
                         }
                     };
+                    // the further tap of a phase-0 sample, on window row 0 or 2h: the weight of the class pair's last row (equal
+                    // to its first: the phase-0 profile is symmetric)
+                    auto extra_tap = [&](const float4 a, const int row) {
+                        const unsigned cx = (__float_as_uint(a.w) - (unsigned)(CT_Q_OFFSET + K * CP.rowp)) / (unsigned)BLK;
+                        const float we = lds_blob1(sbase + CP.eoff + (cx * ROWS + (unsigned)(H - d)) * 4u);
+                        if (row == 0) tap(0, a.x, a.y, a.z, we);
+                        else tap(ROWS - 1, a.x, a.y, a.z, we);
+                    };
                     typedef std::integral_constant<int, 0> I_0;
                     typedef std::integral_constant<int, LIVE> I_LIVE;
                     // n consecutive samples / the samples whose bits are set, all of one kind
@@ -758,15 +774,26 @@ __global__ void __launch_bounds__(TW, PBRT_CLASS_RESIDENT_THREADS / TW) splat_cl
                         }
                     };
                     if (simple_rows && (interior || (d == -H ? simple_right : simple_left))) {
-                        // up-run with taps [U0, U1), then down-run with taps [D0, D1)
-                        auto visit = [&](auto u0, auto u1, auto d0, auto d1) {
-                            if (interior) {
-                                run(pa, n_up, std::false_type{}, u0, u1);
-                                run(pa + n_up, spp - n_up, std::true_type{}, d0, d1);
-                            } else {
-                                run_bits(run_up, std::false_type{}, u0, u1);
-                                run_bits(run_down, std::true_type{}, d0, d1);
+                        // up-run with taps [U0, U1), then down-run with taps [D0, D1).  A phase-0 sample runs as the kind of
+                        // its index; its one further tap keeps the stream's order per pixel: window row 2h (which only
+                        // "down" samples touch otherwise) right after the up-run, row 0 (only "up" samples) after it too.
+                        const unsigned eb_all = m_both & (interior ? sppmask : (d == -H ? m_rall : m_lall));
+                        auto extras = [&](unsigned eb, const int row) {
+                            while (eb) {
+                                const int s0 = __ffs((int)eb) - 1;
+                                eb &= eb - 1;
+                                if ((pf[s0] & CF_BOTH) == CF_BOTH) extra_tap(pa[s0], row);
                             }
+                        };
+                        auto visit = [&](auto u0, auto u1, auto d0, auto d1) {
+                            if (interior) run(pa, n_up, std::false_type{}, u0, u1);
+                            else run_bits(run_up, std::false_type{}, u0, u1);
+                            if (eb_all) {
+                                if (band >= 0) extras(eb_all & m_up, ROWS - 1);
+                                if (band <= 0) extras(eb_all & ~m_up, 0);
+                            }
+                            if (interior) run(pa + n_up, spp - n_up, std::true_type{}, d0, d1);
+                            else run_bits(run_down, std::true_type{}, d0, d1);
                         };
                         // Halo rows: the b-th sample row above the segment reaches window rows >= H + b only — taps
                         // [H + b, LIVE) of "up", [H + b - 1, LIVE) of "down"; the b-th below, window rows <= H - b —
@@ -793,6 +820,10 @@ __global__ void __launch_bounds__(TW, PBRT_CLASS_RESIDENT_THREADS / TW) splat_cl
                         else below(std::integral_constant<int, (H == 4 ? 4 : 1)>{});
                         continue;
                     }
+                    // (from here on the uniform runs leave out the indices that may hold a phase-0 sample: `general` adds
+                    // its extra tap)
+                    run_up &= ~m_both;
+                    run_down &= ~m_both;
                     // a sample of any kind, decided per lane
                     auto general = [&](const int s, const int c0) {
                         const float4 a = pa[s];
@@ -808,14 +839,11 @@ __global__ void __launch_bounds__(TW, PBRT_CLASS_RESIDENT_THREADS / TW) splat_cl
                         }
                         if (d == -H && !(fl & CF_RIGHT)) return;
                         if (d == H && !(fl & CF_LEFT)) return;
-                        if (fl & CF_DOWN) {
-                            body(a, std::true_type{}, I_0{}, I_LIVE{});
-                        } else {
+                        if (fl & CF_UP) {
                             body(a, std::false_type{}, I_0{}, I_LIVE{});
-                            if (fl & CF_BOTH) {  // phase 0: the last window row as well
-                                const unsigned cx = (__float_as_uint(a.w) - (unsigned)(CT_Q_OFFSET + K * CP.rowp)) / (unsigned)BLK;
-                                tap(ROWS - 1, a.x, a.y, a.z, lds_blob1(sbase + CP.eoff + (cx * ROWS + (unsigned)(H - d)) * 4u));
-                            }
+                            if (fl & CF_DOWN) extra_tap(a, ROWS - 1);  // phase 0: the last window row as well
+                        } else {
+                            body(a, std::true_type{}, I_0{}, I_LIVE{});
                         }
                     };
                     // one segment: a run of consecutive indices (always, at an interior column) or scattered ones

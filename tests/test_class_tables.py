@@ -14,7 +14,7 @@ import pytest
 import oracle
 from oracle import OracleFilm
 
-CF_DOWN, CF_BOTH, CF_LEFT, CF_RIGHT = 1, 2, 4, 8
+CF_UP, CF_DOWN, CF_LEFT, CF_RIGHT = 1, 2, 4, 8
 FAST_ENTRIES, CARE_ENTRIES = 32, 16
 LUT_Y, LUT_X, CARE_Y, CARE_X, Q_OFFSET = 0, 512, 1024, 1536, 2048
 SLOW_X, SLOW_Y = 0x40000000, 0x80000000
@@ -84,14 +84,21 @@ class Replay:
             if v == ROWS - 1 and not fl & CF_RIGHT:
                 continue
             col = self.f32[(meta + v * g["COLB"]) // 4:][:LIVE]
-            if fl & CF_DOWN:
-                for i in range(LIVE):
-                    out[i + 1, v] = col[LIVE - 1 - i]
-            else:
+            assert fl & (CF_UP | CF_DOWN)
+            both = (fl & 3) == 3  # phase 0: either kind, plus the row the other kind would add
+            cx = (meta - (Q_OFFSET + g["K"] * g["ROWP"])) // g["BLK"]
+            if fl & CF_UP:
                 out[:LIVE, v] = col
-                if fl & CF_BOTH:
-                    cx = (meta - (Q_OFFSET + g["K"] * g["ROWP"])) // g["BLK"]
+                if both:
                     out[ROWS - 1, v] = self.f32[g["EOFF"] // 4 + cx * ROWS + v]
+            if fl & CF_DOWN:
+                down = np.zeros(ROWS, dtype=np.float32)
+                for i in range(LIVE):
+                    down[i + 1] = col[LIVE - 1 - i]
+                if both:
+                    down[0] = self.f32[g["EOFF"] // 4 + cx * ROWS + v]
+                    assert np.array_equal(down.view(np.uint32), out[:, v].view(np.uint32))  # the two readings agree
+                out[:, v] = down
         return out
 
 

@@ -293,6 +293,37 @@ def test_full_size_c2_properties(gpu, orc):
     assert rel_err(f3.read_pixels()[:, :4], films[0][:, :4]) <= REL_TOL
 
 
+def test_back_to_back_passes_overlap_without_changing_a_bit(gpu, orc, monkeypatch):
+    """Passes over the same resident streams are launched as programmatic dependents (pass i+1 starts in the SM slots
+    pass i's early CTAs leave and waits for it before touching the film).  Full-size configs[1], three passes: equal,
+    bit for bit, to the same passes with the overlap switched off, and a band of it to the oracle's three passes."""
+    from pbrt_b200 import synth
+
+    res, spp = (1920, 1080), 16
+    filt, kind, rad, p0, p1 = make_filter(gpu, "gaussian")
+    table = oracle.filter_table(orc, kind, rad, p0, p1)
+    b = (0, 0, *res)
+    xy_d, rgbw_d, n = synth.samples(b, spp, seed=3)
+    out = []
+    for no_pdl in ("0", "1"):
+        monkeypatch.setenv("PBRT_B200_NO_PDL", no_pdl)
+        f = gpu.Film.new(res, [[0, 0], [1, 1]], filt, 35.0, "x.pfm", 1.0, float("inf"))
+        for _ in range(3):
+            f.add_samples_tile([[0, 0], list(res)], spp, xy_d, rgbw_d, gpu.SPLAT_EXACT)
+        f.check()
+        out.append(f.read_pixels())
+    assert np.array_equal(u32(out[0]), u32(out[1]))
+    y0, y1, halo = 1020, 1040, 3   # rows around 1024: the pre-pass's power-of-two check tier as well
+    band = (0, y0 - halo, 1920, y1 + halo)
+    xy_b, rgbw_b, nb = synth.samples(band, spp, seed=3, index_bounds=b)
+    of = OracleFilm(orc, res, [0, y0 / 1080, 1, y1 / 1080], rad, table)
+    assert of.cropped() == (0, y0, 1920, y1)
+    for _ in range(3):
+        of.add_samples_pass(band, spp, xy_b.to_numpy(np.float32, (nb, 2)), rgbw_b.to_numpy(np.float32, (nb, 4)), threads=8)
+    got = out[0].reshape(1080, 1920, 7)[y0:y1].reshape(-1, 7)
+    assert np.array_equal(u32(got), u32(of.pixels()))
+
+
 @pytest.mark.parametrize("name", list(oracle.FILTERS))
 def test_c1_matches_committed_golden(gpu, name):
     """CUDA path against the committed fixture alone (no oracle call): device sample generator -> splat -> resolve."""
