@@ -658,13 +658,15 @@ __global__ void __launch_bounds__(TW, PBRT_CLASS_RESIDENT_THREADS / TW) splat_cl
             }
             // per sample index: is every sample of the strip "up" / "down", does every / no sample reach the outermost
             // column on the left / right.  Words: 0 !up 1 !down 2 !left-all 3 !left-none 4 !right-all 5 !right-none
-            // 6 some sample may have phase 0 (its extra tap follows the run it is in)
+            // 6 some sample may have phase 0 on y (its extra tap follows the run it is in)  7 ... on x (it reaches both
+            // outermost columns: taken per lane among the uniform samples of an edge-column visit)
             unsigned *mk = s_mask + parity * 8;
             if (mask_mode && tid < nstaged) {
                 const unsigned bit = 1u << r0;
                 if (!(andf & CF_UP)) atomicOr(&mk[0], bit);
                 if (!(andf & CF_DOWN)) atomicOr(&mk[1], bit);
                 if ((orf & CF_BOTH) == CF_BOTH) atomicOr(&mk[6], bit);
+                if ((orf & (CF_LEFT | CF_RIGHT)) == (CF_LEFT | CF_RIGHT)) atomicOr(&mk[7], bit);
                 if (!(andf & CF_LEFT)) atomicOr(&mk[2], bit);
                 if (orf & CF_LEFT) atomicOr(&mk[3], bit);
                 if (!(andf & CF_RIGHT)) atomicOr(&mk[4], bit);
@@ -692,13 +694,15 @@ __global__ void __launch_bounds__(TW, PBRT_CLASS_RESIDENT_THREADS / TW) splat_cl
                 const unsigned m_up = mask_mode ? ~mk[0] & sppmask : 0u, m_down = mask_mode ? ~mk[1] & sppmask : 0u;
                 const unsigned m_lall = ~mk[2] & sppmask, m_lnone = mask_mode ? ~mk[3] & sppmask : 0u;
                 const unsigned m_rall = ~mk[4] & sppmask, m_rnone = mask_mode ? ~mk[5] & sppmask : 0u;
-                const unsigned m_both = mk[6] & sppmask;
+                const unsigned m_both = mk[6] & sppmask, m_xboth = mk[7] & sppmask;
                 // A "simple" row (every stratified row without a phase-0 or classless sample): sample indices 0..n_up-1 are
                 // "up" everywhere in the strip, the rest "down", and each index either always or never reaches an
                 // outermost column.  Its visits are two loops with no per-sample decisions.
                 const int n_up = __popc(m_up);
                 const bool simple_rows = mask_mode && m_up == ((1u << n_up) - 1u) && (m_up | m_down) == sppmask;
-                const bool simple_left = (m_lall | m_lnone) == sppmask, simple_right = (m_rall | m_rnone) == sppmask;
+                // outermost columns: every index reaches its left one throughout, or its right one throughout (a sample on
+                // x phase 0 reaches both and fits either)
+                const bool simple_edges = (m_lall | m_rall) == sppmask;
                 // Halo rows (sample rows above / below the output rows of this CTA) reach only a few owned rows: window
                 // rows j >= H + t for the t-th row above, j <= H - b for the b-th row below.  Computing more is harmless
                 // (rows that are not owned are never flushed), so this only selects cheaper bodies.
@@ -757,6 +761,9 @@ __global__ void __launch_bounds__(TW, PBRT_CLASS_RESIDENT_THREADS / TW) splat_cl
 #pragma unroll (H == 4 ? kClassUnroll4 : kClassUnroll)
                         for (int i = 0; i < n; ++i) body(q[i], down_tag, i0_tag, i1_tag);
                     };
+                    // the samples whose bits are set; those of `lane` per lane: only a sample that itself reaches this
+                    // outermost column (x phase 0 among samples that reach the other one)
+                    const unsigned reach = d == -H ? CF_RIGHT : (d == H ? CF_LEFT : 0u);
                     auto run_bits = [&](unsigned bits, auto down_tag, auto i0_tag, auto i1_tag) {
                         if (decltype(i0_tag)::value >= decltype(i1_tag)::value) return;
                         while (bits) {  // two at a time where neighbours are set (stratified streams: always)
@@ -773,27 +780,41 @@ __global__ void __launch_bounds__(TW, PBRT_CLASS_RESIDENT_THREADS / TW) splat_cl
                             }
                         }
                     };
-                    if (simple_rows && (interior || (d == -H ? simple_right : simple_left))) {
+                    // the same with some indices (`lane`) taken per lane (rows that hold an x phase-0 sample)
+                    auto run_bits_lane = [&](unsigned bits, const unsigned lane, auto down_tag, auto i0_tag, auto i1_tag) {
+                        if (decltype(i0_tag)::value >= decltype(i1_tag)::value) return;
+                        while (bits) {
+                            const int s0 = __ffs((int)bits) - 1;
+                            bits &= bits - 1;
+                            if (!((lane >> s0) & 1u) || (pf[s0] & reach)) body(pa[s0], down_tag, i0_tag, i1_tag);
+                        }
+                    };
+                    if (simple_rows && (interior || simple_edges)) {
                         // up-run with taps [U0, U1), then down-run with taps [D0, D1).  A phase-0 sample runs as the kind of
                         // its index; its one further tap keeps the stream's order per pixel: window row 2h (which only
                         // "down" samples touch otherwise) right after the up-run, row 0 (only "up" samples) after it too.
-                        const unsigned eb_all = m_both & (interior ? sppmask : (d == -H ? m_rall : m_lall));
+                        const unsigned uni = d == -H ? m_rall : m_lall;             // edge column: every sample of the index reaches it
+                        const unsigned lane = interior ? 0u : m_xboth & ~uni;        // ... only samples on x phase 0 do
+                        const unsigned eb_all = m_both & (interior ? sppmask : (uni | lane));
                         auto extras = [&](unsigned eb, const int row) {
                             while (eb) {
                                 const int s0 = __ffs((int)eb) - 1;
                                 eb &= eb - 1;
-                                if ((pf[s0] & CF_BOTH) == CF_BOTH) extra_tap(pa[s0], row);
+                                const unsigned fl = pf[s0];
+                                if ((fl & CF_BOTH) == CF_BOTH && (fl & reach) == reach) extra_tap(pa[s0], row);
                             }
                         };
                         auto visit = [&](auto u0, auto u1, auto d0, auto d1) {
                             if (interior) run(pa, n_up, std::false_type{}, u0, u1);
-                            else run_bits(run_up, std::false_type{}, u0, u1);
+                            else if (lane) run_bits_lane(m_up & (uni | lane), lane, std::false_type{}, u0, u1);
+                            else run_bits(m_up & uni, std::false_type{}, u0, u1);
                             if (eb_all) {
                                 if (band >= 0) extras(eb_all & m_up, ROWS - 1);
                                 if (band <= 0) extras(eb_all & ~m_up, 0);
                             }
                             if (interior) run(pa + n_up, spp - n_up, std::true_type{}, d0, d1);
-                            else run_bits(run_down, std::true_type{}, d0, d1);
+                            else if (lane) run_bits_lane(m_down & (uni | lane), lane, std::true_type{}, d0, d1);
+                            else run_bits(m_down & uni, std::true_type{}, d0, d1);
                         };
                         // Halo rows: the b-th sample row above the segment reaches window rows >= H + b only — taps
                         // [H + b, LIVE) of "up", [H + b - 1, LIVE) of "down"; the b-th below, window rows <= H - b —
