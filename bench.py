@@ -419,7 +419,28 @@ def main():
         dt = torch.tensor([(time.perf_counter() - t0) / k], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        # the host link's own ceiling, measured the same way in the same run: every rank copies the same number of
+        # bytes from pinned memory with plain cudaMemcpyAsync, all ranks at once (nothing else running)
+        h2d_bytes = n_local * (20 if weights_all_one else 24)
+        hsrc = torch.empty(h2d_bytes, dtype=torch.uint8, pin_memory=True)
+        ddst = torch.empty(h2d_bytes, dtype=torch.uint8, device="cuda")
+        ddst.copy_(hsrc, non_blocking=True)
+        barrier()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record(stream)
+        for _ in range(5):
+            ddst.copy_(hsrc, non_blocking=True)
+        c1.record(stream)
+        barrier()
+        ct = torch.tensor([c0.elapsed_time(c1) / 5.0], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(ct, op=dist.ReduceOp.MAX)
+        h2d_ceiling = world * h2d_bytes / (float(ct.item()) * 1e-3) / 1e9
+        h2d_achieved = world * h2d_bytes / float(dt.item()) / 1e9
+        del hsrc, ddst
         e2e = {"value": n_unique_total / float(dt.item()), "unit": "samples/s",
+               "h2d_gbs": h2d_achieved, "h2d_ceiling_gbs": h2d_ceiling, "frac_of_h2d_ceiling": h2d_achieved / h2d_ceiling,
+               "h2d_ceiling_note": "aggregate over all ranks of plain pinned cudaMemcpyAsync uploads of the step's bytes, every rank at once, measured in this run",
                "h2d_bytes_per_step": n_local * (20 if weights_all_one else 24), "d2h_bytes_per_step": max(owned.area(), 0) * 12,
                "ms_per_step": float(dt.item()) * 1e3,
                "api": "Film.add_samples_tile_rgb(pinned host xy, rgb, sample_weight=%s) + Film.resolve_rgb(pinned host out), transfers enqueued, one synchronize after the K steps" % ("None: all weights are 1" if weights_all_one else "pinned host stream")}
@@ -635,6 +656,26 @@ def time_extras(pb, synth, film, torch, stream, peak, xy_main=None, rgbw_main=No
         del xy_t, rgbw_t, sidx, order
     except Exception as e:
         out["splat_tiles_16x16"] = {"error": f"{type(e).__name__}: {e}"}
+    # the shapes the class kernel does not serve: the reference's own test filter (box r = 8: generic gather) and a
+    # pixel-major stream of 64 spp handed over in one call (window kernel on 32-column strips)
+    try:
+        from pbrt_b200 import synth as _synth
+        for key, filt, res, spp_x, note in (
+                ("splat_box_r8_generic", pb.BoxFilter([8.0, 8.0]), (1920, 1080), 4,
+                 "box r=8 (src/core/film.rs:505-521), 4 spp: splat_gather_generic_kernel, thread per output pixel"),
+                ("splat_mitchell_spp64_one_call", pb.MitchellFilter([2.0, 2.0], 1.0 / 3.0, 1.0 / 3.0), (3840, 540), 64,
+                 "Mitchell r=2, 64 spp in ONE pixel-major call (a quarter-height band of configs[2]): splat_window_kernel on 32-column strips")):
+            f2 = pb.Film.new(list(res), [[0, 0], [1, 1]], filt, 35.0, "extras_x.pfm", 1.0, float("inf"))
+            b4 = f2.cropped_pixel_bounds.as4()
+            xy_x, rgbw_x, n_x = _synth.samples(b4, spp_x, seed=2)
+            sbl = [[b4[0], b4[1]], [b4[2], b4[3]]]
+            ms = timed(lambda: f2.add_samples_tile(sbl, spp_x, xy_x, rgbw_x, pb.SPLAT_EXACT), reps=3)
+            f2.check()
+            out[key] = {"samples_per_s": n_x / (ms * 1e-3), "ms": ms, "film": list(res), "spp": spp_x, "note": note}
+            f2.close()
+            del xy_x, rgbw_x
+    except Exception as e:
+        out["splat_other_shapes"] = {"error": f"{type(e).__name__}: {e}"}
     # a14: 1e8 lookups, alternating between two buffers so that no launch finds its lines in L2 (2 x 400 MB, 2 x 1.2 GB)
     n = 100_000_000
     t1 = [torch.empty(n, dtype=torch.float32, device="cuda") for _ in range(2)]

@@ -111,6 +111,8 @@ lib.pbrt_b200_debug_force_generic_splat.restype = C.c_int
 lib.pbrt_b200_debug_force_generic_splat.argtypes = [C.c_int]
 lib.pbrt_b200_debug_class_tables.restype = C.c_int
 lib.pbrt_b200_debug_class_tables.argtypes = [_f32p, C.c_float, C.c_float, C.POINTER(C.c_uint8), C.c_int, _i32p]
+lib.pbrt_b200_debug_class_segments.restype = C.c_int
+lib.pbrt_b200_debug_class_segments.argtypes = [C.c_int] * 7 + [_i32p]
 
 
 def last_error() -> str:

@@ -955,26 +955,51 @@ static int g_trace_n = 0, g_trace_cols = 0;
 // idles to the end of the kernel (per-CTA trace: tools/cta_trace.py, profiles/r2_cta_trace.txt).  CTAs are placed
 // round-robin by linear block id, so the residency rank of a segment's CTAs is (blockIdx.y * cols + x) / SMs; segments
 // of a slower rank get fewer rows: rows + c = T * w[rank], c = the cost of the 2h halo sample rows in row units.
+static double g_rank_w[8] = {1.0, 0.97, 0.93, 0.885, 0.85, 0.82, 0.79, 0.76};  // measured on C2 / C3 / C5, back-to-back launches
+static double g_halo_c = -1.0;
+
+// host only: first row of each of `segs` segments of [y0, y0 + rows), one past the last at [segs]
+static void class_segment_rows(int y0, int rows, int cols, int segs, int per_sm, int H, int nsm, std::vector<int> *out) {
+    if (g_halo_c < 0.0) {
+        g_halo_c = 1.2;
+        if (const char *v = getenv("PBRT_B200_HALO_C")) g_halo_c = atof(v);
+        if (const char *v = getenv("PBRT_B200_RANK_W")) {
+            int i = 0;
+            for (const char *q = v; *q && i < 8; ++i) {
+                g_rank_w[i] = atof(q);
+                while (*q && *q != ',') ++q;
+                if (*q == ',') ++q;
+            }
+            for (; i < 8 && i > 0; ++i) g_rank_w[i] = g_rank_w[i - 1];
+        }
+    }
+    std::vector<double> ws(segs);
+    double wsum = 0.0;
+    for (int s = 0; s < segs; ++s) {
+        const int rank = std::min(std::max(std::min(per_sm, 8), 1) - 1, (s * cols + cols / 2) / std::max(nsm, 1));
+        ws[s] = g_rank_w[rank];
+        wsum += ws[s];
+    }
+    const double c = g_halo_c * H, T = (rows + segs * c) / wsum;
+    std::vector<int> &host = *out;
+    host.assign(segs + 1, 0);
+    double acc = 0.0;
+    for (int s = 0; s < segs; ++s) {
+        host[s] = (int)(acc + 0.5);
+        acc += std::max(1.0, T * ws[s] - c);
+    }
+    host[segs] = rows;
+    // every segment keeps at least one row (segs <= rows)
+    for (int s = 1; s < segs; ++s) host[s] = std::max(host[s], host[s - 1] + 1);
+    for (int s = segs - 1; s > 0; --s) host[s] = std::min(host[s], host[s + 1] - 1);
+    for (int s = 0; s <= segs; ++s) host[s] += y0;
+}
+
 static cudaError_t class_segments(int y0, int rows, int cols, int segs, int per_sm, int H, const int **d_out) {
     static int *d_seg = nullptr;
     static int cap = 0;
     static std::vector<int> host;
     static int key[7] = {-1, -1, -1, -1, -1, -1, -1};
-    static double w[8] = {1.0, 0.97, 0.93, 0.885, 0.85, 0.82, 0.79, 0.76};  // measured on C2 / C3 / C5, back-to-back launches
-    static double halo_c = -1.0;
-    if (halo_c < 0.0) {
-        halo_c = 1.2;
-        if (const char *v = getenv("PBRT_B200_HALO_C")) halo_c = atof(v);
-        if (const char *v = getenv("PBRT_B200_RANK_W")) {
-            int i = 0;
-            for (const char *q = v; *q && i < 8; ++i) {
-                w[i] = atof(q);
-                while (*q && *q != ',') ++q;
-                if (*q == ',') ++q;
-            }
-            for (; i < 8 && i > 0; ++i) w[i] = w[i - 1];
-        }
-    }
     const int k[7] = {y0, rows, cols, segs, per_sm, H, ctx().device};
     if (memcmp(k, key, sizeof k) != 0 || !d_seg) {
         if (segs + 1 > cap) {
@@ -985,26 +1010,7 @@ static cudaError_t class_segments(int y0, int rows, int cols, int segs, int per_
             if (e != cudaSuccess) return e;
             cap = segs + 1 + 64;
         }
-        const int nsm = ctx().sm_count;
-        std::vector<double> ws(segs);
-        double wsum = 0.0;
-        for (int s = 0; s < segs; ++s) {
-            const int rank = std::min(std::min(per_sm, 8) - 1, (s * cols + cols / 2) / nsm);
-            ws[s] = w[rank];
-            wsum += ws[s];
-        }
-        const double c = halo_c * H, T = (rows + segs * c) / wsum;
-        host.assign(segs + 1, 0);
-        double acc = 0.0;
-        for (int s = 0; s < segs; ++s) {
-            host[s] = (int)(acc + 0.5);
-            acc += std::max(1.0, T * ws[s] - c);
-        }
-        host[segs] = rows;
-        // every segment keeps at least one row (segs <= rows)
-        for (int s = 1; s < segs; ++s) host[s] = std::max(host[s], host[s - 1] + 1);
-        for (int s = segs - 1; s > 0; --s) host[s] = std::min(host[s], host[s + 1] - 1);
-        for (int s = 0; s <= segs; ++s) host[s] += y0;
+        class_segment_rows(y0, rows, cols, segs, per_sm, H, ctx().sm_count, &host);
         cudaError_t e = cudaMemcpyAsync(d_seg, host.data(), (size_t)(segs + 1) * sizeof(int), cudaMemcpyHostToDevice, ctx().stream);
         if (e != cudaSuccess) return e;
         memcpy(key, k, sizeof k);
@@ -1138,3 +1144,13 @@ extern "C" int pbrt_b200_debug_cta_trace(unsigned long long *out, int cap, int *
     return n;
 }
 #endif
+
+// [UTIL, test hook] the row segments launch_class would give a grid of `cols` strips x `segs` segments over rows
+// [y0, y0 + rows) on a device of `nsm` SMs holding `per_sm` CTAs each (host only): segs + 1 ints
+extern "C" int pbrt_b200_debug_class_segments(int y0, int rows, int cols, int segs, int per_sm, int h, int nsm, int32_t *out) {
+    if (!out || segs < 1 || rows < segs) return 0;
+    std::vector<int> v;
+    pb::class_segment_rows(y0, rows, cols, segs, per_sm, h, nsm, &v);
+    for (int i = 0; i <= segs; ++i) out[i] = v[i];
+    return segs + 1;
+}

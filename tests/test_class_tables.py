@@ -201,3 +201,37 @@ def test_classes_cover_random_phases(pb, orc):
 def test_other_radii_have_no_class_tables(pb, radius):
     blob, g = class_tables(pb, np.ones(256, dtype=np.float32), radius)
     assert blob is None
+
+
+# ---- row segments of the one-wave grid (splat_class.cu: class_segment_rows) ----
+
+def segments(y0, rows, cols, segs, per_sm=4, h=2, nsm=148):
+    from pbrt_b200 import _lib
+
+    out = (C.c_int32 * (segs + 1))()
+    n = _lib.lib.pbrt_b200_debug_class_segments(y0, rows, cols, segs, per_sm, h, nsm, out)
+    assert n == segs + 1
+    return list(out)
+
+
+@pytest.mark.parametrize("y0,rows,cols,segs,h", [(0, 1080, 15, 39, 2), (0, 2160, 30, 19, 2), (0, 4320, 60, 9, 4),
+                                                  (-3, 67, 1, 8, 2), (1080, 540, 60, 9, 4), (5, 33, 2, 33, 2), (0, 1, 1, 1, 2)])
+def test_row_segments_cover_the_rows_once_and_shrink_with_residency_rank(y0, rows, cols, segs, h):
+    s = segments(y0, rows, cols, segs, h=h)
+    assert s[0] == y0 and s[-1] == y0 + rows
+    sizes = [b - a for a, b in zip(s, s[1:])]
+    assert min(sizes) >= 1 and sum(sizes) == rows
+    # CTAs are placed round-robin by linear block id: a segment's rank on its SM is (segment * cols + x) / SMs
+    ranks = [min(3, (i * cols + cols // 2) // 148) for i in range(segs)]
+    by_rank = {}
+    for r, n in zip(ranks, sizes):
+        by_rank.setdefault(r, []).append(n)
+    means = [sum(v) / len(v) for _, v in sorted(by_rank.items())]
+    if rows >= 8 * segs:  # (tiny grids are all rounding)
+        assert all(a >= b for a, b in zip(means, means[1:])), means        # an older CTA runs faster and gets more rows
+        assert max(sizes) - min(sizes) <= max(2, round(0.2 * rows / segs)), sizes
+
+
+def test_row_segments_of_a_grid_smaller_than_the_machine_are_equal():
+    sizes = [b - a for a, b in zip(*(lambda s: (s, s[1:]))(segments(0, 640, 4, 16)))]   # 64 CTAs on 148 SMs: all rank 0
+    assert max(sizes) - min(sizes) <= 1
