@@ -594,13 +594,11 @@ __global__ void __launch_bounds__(TW, PBRT_CLASS_RESIDENT_THREADS / TW) splat_cl
             typedef std::integral_constant<int, 0> T_PLAIN;
             typedef std::integral_constant<int, 1> T_CHECK;
             typedef std::integral_constant<int, 2> T_CAREFUL;
-            const float2 *lxy = gxy + tid;  // this thread's next sample; the batch is lxy[0], lxy[TW], ...
-            const float4 *lrgbw = grgbw + tid;
-            for (int e0 = tid; e0 < nstaged; e0 += U * TW, lxy += U * TW, lrgbw += U * TW) {
-                float2 p[U];
-                float4 L[U];
-                const bool full = e0 + (U - 1) * TW < nstaged;
-                if (full) {
+            // the batch of sample e0 (this thread's), e0 + TW, ...: loads, then classification
+            auto load_batch = [&](float2 *p, float4 *L, const int e0) {
+                const float2 *lxy = gxy + e0;
+                const float4 *lrgbw = grgbw + e0;
+                if (e0 + (U - 1) * TW < nstaged) {
 #pragma unroll
                     for (int u = 0; u < U; ++u) {
                         p[u] = ldg_stream(lxy + u * TW);
@@ -615,6 +613,9 @@ __global__ void __launch_bounds__(TW, PBRT_CLASS_RESIDENT_THREADS / TW) splat_cl
                         }
                     }
                 }
+            };
+            auto process_batch = [&](float2 *p, float4 *L, const int e0) {
+                const bool full = e0 + (U - 1) * TW < nstaged;
                 if (clamp_on) {
 #pragma unroll
                     for (int u = 0; u < U; ++u)
@@ -655,6 +656,12 @@ __global__ void __launch_bounds__(TW, PBRT_CLASS_RESIDENT_THREADS / TW) splat_cl
                         fnxh += fdq;
                     }
                 }
+            };
+            for (int e0 = tid; e0 < nstaged; e0 += U * TW) {
+                float2 p[U];
+                float4 L[U];
+                load_batch(p, L, e0);
+                process_batch(p, L, e0);
             }
             // per sample index: is every sample of the strip "up" / "down", does every / no sample reach the outermost
             // column on the left / right.  Words: 0 !up 1 !down 2 !left-all 3 !left-none 4 !right-all 5 !right-none
