@@ -1093,8 +1093,16 @@ static int class_pick_width(const ClassParams &CP) {
     if (force == 64) return launch_class<H, 64, FMA>(CP);
     if (force == 32) return launch_class<H, 32, FMA>(CP);
     const int spp = CP.S.spp;
-    if (ClassSmem<H, 128>::bytes(CP.blob_bytes, spp) * 2 <= 226 * 1024) return launch_class<H, 128, FMA>(CP);
-    if (ClassSmem<H, 64>::bytes(CP.blob_bytes, spp) * 2 <= 226 * 1024) return launch_class<H, 64, FMA>(CP);
+    // widest strip of which two CTAs fit an SM — among the widths spp divides, if any: a thread then keeps its sample
+    // index along a row and the row can run on the uniform path (24 spp: 96 columns 2.2 x the rate of 128)
+    const bool fit128 = ClassSmem<H, 128>::bytes(CP.blob_bytes, spp) * 2 <= 226 * 1024;
+    const bool fit96 = ClassSmem<H, 96>::bytes(CP.blob_bytes, spp) * 2 <= 226 * 1024;
+    const bool fit64 = ClassSmem<H, 64>::bytes(CP.blob_bytes, spp) * 2 <= 226 * 1024;
+    if (fit128 && 128 % spp == 0) return launch_class<H, 128, FMA>(CP);
+    if (fit96 && 96 % spp == 0) return launch_class<H, 96, FMA>(CP);
+    if (fit64 && 64 % spp == 0) return launch_class<H, 64, FMA>(CP);
+    if (fit128) return launch_class<H, 128, FMA>(CP);
+    if (fit64) return launch_class<H, 64, FMA>(CP);
     return launch_class<H, 32, FMA>(CP);
 #endif
 }

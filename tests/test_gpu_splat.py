@@ -123,6 +123,15 @@ def test_large_spp_uses_narrower_strips_exact(gpu, orc, spp):
     assert np.array_equal(u32(film.read_pixels()), u32(of.pixels()))
 
 
+@pytest.mark.parametrize("name", ["gaussian", "lanczos"])
+@pytest.mark.parametrize("spp", [1, 3, 6, 12, 20, 24, 32])
+def test_samples_per_pixel_the_strip_width_is_chosen_for(gpu, orc, name, spp):
+    """The class kernel picks 128 / 96 / 64 columns so that spp divides the strip (a thread keeps its sample index:
+    uniform path) and otherwise runs every sample per lane: 1..32 spp at radius 2 and 4, a film wider than two strips."""
+    film, of = run_pair(gpu, orc, name, (300, 21), [0, 0, 1, 1], (-2, -2, 302, 23), spp, gpu.SPLAT_EXACT, seed=spp)
+    assert np.array_equal(u32(film.read_pixels()), u32(of.pixels()))
+
+
 @pytest.mark.parametrize("radius", [(8.0, 8.0), (2.0, 3.0), (0.3, 0.3), (5.0, 5.0)])
 def test_radii_served_by_the_generic_gather(gpu, orc, radius):
     film, of = run_pair(gpu, orc, "triangle", (48, 40), [0, 0, 1, 1], (0, 0, 48, 40), 4, gpu.SPLAT_EXACT, radius=radius)

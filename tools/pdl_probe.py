@@ -18,6 +18,8 @@ if len(sys.argv) > 3:  # e.g. "1920x2160:0,0.5,1,1": another film size and crop 
     W, H = (int(v) for v in r.split("x"))
     c = [float(v) for v in c.split(",")]
     crop = [[c[0], c[1]], [c[2], c[3]]]
+if len(sys.argv) > 4:
+    spp = int(sys.argv[4])
 cls = {"gaussian": pb.GaussianFilter, "mitchell": pb.MitchellFilter, "lanczos": pb.LanczosSincFilter}[wl["filter"]]
 filt = cls(wl["radius"], wl["p0"], wl["p1"]) if wl["filter"] == "mitchell" else cls(wl["radius"], wl["p0"])
 film = pb.Film.new([W, H], crop, filt, 35.0, "t.pfm", 1.0, float("inf"))
