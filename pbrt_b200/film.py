@@ -207,6 +207,9 @@ class Film:
             else:     # any other order: scatter (order of additions not fixed)
                 self.add_samples(tile._sample_bounds, xy, rgbw)
             tile._samples_xy, tile._samples_rgbw = [], []
+            # a broken add_sample contract (sample outside its nominal pixel, non-finite radiance) surfaces here, where the
+            # reference's debug_assert!s would have fired, not at some later check()
+            self.check()
         _lib.check(
             _lib.lib.pbrt_film_merge_tile(
                 self._h, _lib.i32x4(tile.pixel_bounds.as4()), tile.pixels.ctypes.data_as(C.c_void_p), 0

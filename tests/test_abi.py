@@ -197,3 +197,21 @@ def test_splat_window_kernels_do_not_spill_and_keep_their_occupancy(pb):
         if m and int(m.group(2)) == 128 and int(m.group(1)) <= 3:
             assert int(regs) <= 128, (name, regs)
     assert found >= 16
+
+
+def test_splat_class_kernels_keep_four_ctas_per_sm(pb):
+    """The hot kernel: every 128-column splat_class_kernel variant must stay within the 128 registers that four resident
+    CTAs per SM allow, and the radius-2 variants (BASELINE configs[1] and [2]) must not spill at all."""
+    from pbrt_b200 import _lib
+
+    out = subprocess.run(["cuobjdump", "--dump-resource-usage", str(_lib.LIB_PATH)], capture_output=True, text=True).stdout
+    found = 0
+    for name, regs, local in re.findall(r"Function (\S*splat_class_kernel\S*):\s*\n\s*REG:(\d+) .*?LOCAL:(\d+)", out):
+        m = re.search(r"ILi(\d)ELi(\d+)ELb", name)
+        if not m or int(m.group(2)) != 128:
+            continue
+        found += 1
+        assert int(regs) <= 128, (name, regs)
+        if int(m.group(1)) == 2:
+            assert int(local) == 0, (name, "spills to local memory")
+    assert found >= 4

@@ -485,6 +485,19 @@ def test_filmtile_add_sample_in_renderer_order_is_exact(gpu, orc):
     assert np.array_equal(u32(film.read_pixels()), u32(of.pixels()))
 
 
+def test_filmtile_add_sample_with_non_finite_radiance_fails_at_the_merge(gpu):
+    """merge_film_tile flushes the samples FilmTile.add_sample recorded and checks the film: a contract violation
+    surfaces at the call that caused it (the reference's debug_assert!s), not at a later check()."""
+    filt, *_ = make_filter(gpu, "gaussian")
+    film = gpu.Film.new((16, 16), [[0, 0], [1, 1]], filt, 35.0, "x.pfm", 1.0, float("inf"))
+    tile = film.get_film_tile([[4, 4], [6, 6]])
+    for y in range(4, 6):
+        for x in range(4, 6):
+            tile.add_sample((x + 0.5, y + 0.5), (float("nan"), 1.0, 1.0), 1.0)
+    with pytest.raises(Exception):
+        film.merge_film_tile(tile)
+
+
 def test_pinned_async_pipeline_equals_synchronous_calls(gpu, orc):
     """PBRT_MEM_PINNED_ASYNC: uploads double-buffered on the copy stream, read-back enqueued; same film, same frames."""
     res, spp = (128, 96), 4
