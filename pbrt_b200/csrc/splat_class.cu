@@ -697,7 +697,11 @@ __global__ void __launch_bounds__(TW, PBRT_CLASS_RESIDENT_THREADS / TW) splat_cl
                 px = P.film[fo];
             }
             // ---------------- gather: this thread's column against the row ----------------
+#ifdef PBRT_CLASS_TIMING_NO_GATHER  // timing probe (results wrong): pre-pass and flush only
+            if (col_ok && ny == cy0 - H) {
+#else
             if (col_ok) {
+#endif
                 const unsigned m_up = mask_mode ? ~mk[0] & sppmask : 0u, m_down = mask_mode ? ~mk[1] & sppmask : 0u;
                 const unsigned m_lall = ~mk[2] & sppmask, m_lnone = mask_mode ? ~mk[3] & sppmask : 0u;
                 const unsigned m_rall = ~mk[4] & sppmask, m_rnone = mask_mode ? ~mk[5] & sppmask : 0u;
