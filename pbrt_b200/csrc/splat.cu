@@ -576,6 +576,96 @@ static int pick_window(const SplatParams &P, int h) {
     return -1;
 }
 
+// The same scatter with warp-aggregated atomics (PBRT_B200_ATOMIC_AGG=1; kept for the ncu comparison of DESIGN.md 5.5):
+// a thread per SAMPLE, so that the lanes of a warp hold consecutive samples of one or two pixels and every tap of theirs
+// goes to the same destination pixel; a segmented shuffle reduction over the run of lanes of a pixel leaves one shared
+// atomic per run, tap and channel instead of one per lane.  The order of additions is a tree: tolerance mode only.
+__global__ void __launch_bounds__(256) splat_atomic_agg_kernel(SplatParams P, int hx, int hy, float4 *__restrict__ scratch) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    float *s_table = reinterpret_cast<float *>(smem);
+    float *s_tile = s_table + 256;
+    const int tw = AT_W + 2 * hx, th = AT_H + 2 * hy;
+    for (int i = threadIdx.x; i < 256; i += 256) s_table[i] = P.table[i];
+    for (int i = threadIdx.x; i < tw * th * 4; i += 256) s_tile[i] = 0.f;
+    __syncthreads();
+    const int bx0 = P.sb.x0 + blockIdx.x * AT_W, by0 = P.sb.y0 + blockIdx.y * AT_H;
+    const int nw = min(AT_W, P.sb.x1 - bx0), nh = min(AT_H, P.sb.y1 - by0);
+    const int W = P.sb.x1 - P.sb.x0, spp = P.spp;
+    const int ox = bx0 - hx, oy = by0 - hy;  // film coords of smem tile origin
+    const int nsamp = nw * nh * spp;
+    const int lane = threadIdx.x & 31;
+    for (int e0 = 0; e0 < nsamp; e0 += 256) {
+        const int e = e0 + threadIdx.x;
+        const bool valid = e < nsamp;
+        const int pix = valid ? e / spp : -1 - lane;  // invalid lanes: runs of their own
+        const int s = e - (valid ? pix : 0) * spp;
+        const int nx = bx0 + (valid ? pix % nw : 0), ny = by0 + (valid ? pix / nw : 0);
+        float cr = 0.f, cg = 0.f, cb = 0.f, dx = 0.f, dy = 0.f;
+        int p0x = 0, p1x = 0, p0y = 0, p1y = 0;
+        if (valid) {
+            const size_t idx = ((size_t)(ny - P.sb.y0) * W + (nx - P.sb.x0)) * (size_t)spp + s;
+            const float2 p = P.xy[idx];
+            float4 L = P.rgbw[idx];
+            if (!(p.x >= (float)nx && p.x <= (float)(nx + 1) && p.y >= (float)ny && p.y <= (float)(ny + 1)))
+                atomicOr(P.err, ERRBIT_NOT_PIXEL_MAJOR);
+            clamp_luminance(L, P.max_lum);
+            dx = p.x - 0.5f; dy = p.y - 0.5f;
+            p0x = max(max(__float2int_ru(dx - P.rx), P.tb.x0), ox);
+            p0y = max(max(__float2int_ru(dy - P.ry), P.tb.y0), oy);
+            p1x = min(min(__float2int_rd(dx + P.rx) + 1, P.tb.x1), ox + tw);
+            p1y = min(min(__float2int_rd(dy + P.ry) + 1, P.tb.y1), oy + th);
+            cr = L.x * L.w; cg = L.y * L.w; cb = L.z * L.w;
+            const float z = cr * 0.f + cg * 0.f + cb * 0.f;
+            if (z != z) atomicOr(P.err, ERRBIT_NONFINITE);
+        }
+        // lanes of one pixel are a contiguous run: which partners of the doubling steps belong to this lane's run
+        unsigned same = 0;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            const int other = __shfl_down_sync(0xffffffffu, pix, 1 << k);
+            if (lane + (1 << k) < 32 && other == pix) same |= 1u << k;
+        }
+        const int before = __shfl_up_sync(0xffffffffu, pix, 1);
+        const bool head = valid && (lane == 0 || before != pix);
+        for (int jy = 0; jy <= 2 * hy; ++jy) {
+            const int y = ny - hy + jy;
+            const bool in_y = y >= p0y && y < p1y;
+            const int iy = table_index(((float)y - dy) * P.iry * 16.f);
+            for (int jx = 0; jx <= 2 * hx; ++jx) {
+                const int x = nx - hx + jx;
+                const bool inside = in_y && x >= p0x && x < p1x;
+                const int ix = table_index(((float)x - dx) * P.irx * 16.f);
+                const float w = inside ? s_table[iy * 16 + ix] : 0.f;
+                float v0 = cr * w, v1 = cg * w, v2 = cb * w, v3 = w;
+                const unsigned any = __ballot_sync(0xffffffffu, inside);
+                if (!any) continue;
+#pragma unroll
+                for (int k = 0; k < 5; ++k) {
+                    const float t0 = __shfl_down_sync(0xffffffffu, v0, 1 << k), t1 = __shfl_down_sync(0xffffffffu, v1, 1 << k);
+                    const float t2 = __shfl_down_sync(0xffffffffu, v2, 1 << k), t3 = __shfl_down_sync(0xffffffffu, v3, 1 << k);
+                    if (same & (1u << k)) { v0 += t0; v1 += t1; v2 += t2; v3 += t3; }
+                }
+                // the destination pixel is the same for the whole run; it lies in the tile whenever some lane is inside
+                if (head && x >= max(P.tb.x0, ox) && x < min(P.tb.x1, ox + tw) && y >= max(P.tb.y0, oy) && y < min(P.tb.y1, oy + th) &&
+                    (v3 != 0.f || v0 != 0.f || v1 != 0.f || v2 != 0.f)) {
+                    float *px = s_tile + ((y - oy) * tw + (x - ox)) * 4;
+                    atomicAdd(px + 0, v0); atomicAdd(px + 1, v1); atomicAdd(px + 2, v2); atomicAdd(px + 3, v3);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    const int ttw = P.tb.x1 - P.tb.x0;
+    for (int i = threadIdx.x; i < tw * th; i += 256) {
+        const int x = ox + i % tw, y = oy + i / tw;
+        if (x < P.tb.x0 || x >= P.tb.x1 || y < P.tb.y0 || y >= P.tb.y1) continue;
+        const float *v = s_tile + i * 4;
+        if (v[3] == 0.f && v[0] == 0.f && v[1] == 0.f && v[2] == 0.f) continue;
+        float *o = reinterpret_cast<float *>(&scratch[(size_t)(y - P.tb.y0) * ttw + (x - P.tb.x0)]);
+        atomicAdd(o + 0, v[0]); atomicAdd(o + 1, v[1]); atomicAdd(o + 2, v[2]); atomicAdd(o + 3, v[3]);
+    }
+}
+
 // ---- batched tiles ---------------------------------------------------------------------------
 
 template <int H, bool FMA>
@@ -671,8 +761,19 @@ int launch_splat_tile(PbrtFilm *f, const Bounds &sb, const Bounds &tb, int spp, 
             attr_set = true;
         }
         dim3 grid((bw(sb) + AT_W - 1) / AT_W, (bh(sb) + AT_H - 1) / AT_H);
-        splat_atomic_kernel<<<grid, 256, smem, ctx().stream>>>(P, hx, hy, f->d_scratch_tile);
-        PB_LAUNCH_CHECK("splat_atomic_kernel");
+        const char *agg = getenv("PBRT_B200_ATOMIC_AGG");
+        if (agg && *agg == '1') {
+            static bool agg_attr_set = false;
+            if (!agg_attr_set) {
+                PB_CUDA(cudaFuncSetAttribute(splat_atomic_agg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+                agg_attr_set = true;
+            }
+            splat_atomic_agg_kernel<<<grid, 256, smem, ctx().stream>>>(P, hx, hy, f->d_scratch_tile);
+            PB_LAUNCH_CHECK("splat_atomic_agg_kernel");
+        } else {
+            splat_atomic_kernel<<<grid, 256, smem, ctx().stream>>>(P, hx, hy, f->d_scratch_tile);
+            PB_LAUNCH_CHECK("splat_atomic_kernel");
+        }
         dim3 mgrid((bw(tb) + 255) / 256, std::min(bh(tb), 4096));
         merge_scratch_kernel<<<mgrid, 256, 0, ctx().stream>>>(f->d_xyzw, f->owned, tb, f->d_scratch_tile);
         PB_LAUNCH_CHECK("merge_scratch_kernel");

@@ -83,6 +83,17 @@ def test_c1_tolerance_modes(gpu, orc, name, mode):
         assert np.array_equal(u32(got[:, 3]), u32(want[:, 3]))
 
 
+@pytest.mark.parametrize("name,res,sb,spp", [("gaussian", (64, 64), (0, 0, 64, 64), 4), ("lanczos", (90, 41), (-4, -4, 94, 45), 16),
+                                             ("mitchell", (70, 30), (3, 2, 66, 29), 5), ("box", (40, 40), (0, 0, 40, 40), 1)])
+def test_warp_aggregated_atomic_scatter_within_tolerance(gpu, orc, monkeypatch, name, res, sb, spp):
+    """The shared-atomic scatter with one atomic per run of lanes that hold samples of the same pixel (kept for the ncu
+    comparison, PBRT_B200_ATOMIC_AGG=1): a tree order of additions, inside the north-star tolerance."""
+    monkeypatch.setenv("PBRT_B200_ATOMIC_AGG", "1")
+    film, of = run_pair(gpu, orc, name, res, [0, 0, 1, 1], sb, spp, gpu.SPLAT_ATOMIC)
+    got, want = film.read_pixels(), of.pixels()
+    assert rel_err(got[:, :4], want[:, :4]) <= REL_TOL
+
+
 # ------------------------------------------------------------------ shapes, clipping, ragged edges
 
 CASES = [
