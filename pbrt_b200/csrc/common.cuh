@@ -196,5 +196,6 @@ int launch_splat_tile(PbrtFilm *f, const Bounds &sb, const Bounds &tb, int spp, 
 // (no-op for other radii); launch_splat_class returns -1 when the film / stream shape is not one it serves.
 int class_tables_create(PbrtFilm *f);
 int launch_splat_class(PbrtFilm *f, const SplatParams &P, int mode);
+int launch_splat_class_tiles(PbrtFilm *f, const SplatParams &P, int ntiles, int max_w, int mode);
 
 }  // namespace pb

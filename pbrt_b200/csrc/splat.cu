@@ -711,6 +711,10 @@ int launch_splat_tiles(PbrtFilm *f, int ntiles, const SplatTile *d_tiles, int ma
     P.tile_out = tile_out;
     const int hx = (int)floorf(P.rx + 0.5f), hy = (int)floorf(P.ry + 0.5f);
     if (hx != hy || hx < 1 || hx > 4) return -1;  // caller falls back to one launch per tile
+    {   // radius 2 or 4 and spp dividing 32: the phase-class gather (splat_class.cu); -1 = not served
+        const int rc = launch_splat_class_tiles(f, P, ntiles, max_w, mode);
+        if (rc >= 0) return rc;
+    }
     const bool fma = mode == PBRT_SPLAT_FMA;
     switch (hx) {
     case 1: return fma ? launch_window_batched<1, true>(P, ntiles, max_w, max_h) : launch_window_batched<1, false>(P, ntiles, max_w, max_h);

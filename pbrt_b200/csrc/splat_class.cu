@@ -419,14 +419,30 @@ constexpr int kClassUnroll4 = PBRT_CLASS_UNROLL4;  // h = 4 (twice the taps per 
 #ifndef PBRT_CLASS_RESIDENT_THREADS
 #define PBRT_CLASS_RESIDENT_THREADS 512  // 4 CTAs of 128 threads per SM: 128 registers per thread
 #endif
-template <int H, int TW, bool FMA>
-__global__ void __launch_bounds__(TW, PBRT_CLASS_RESIDENT_THREADS / TW) splat_class_kernel(ClassParams CP) {
+// TILES: the batched form (pbrt_film_add_samples_tiles): blockIdx.z selects a renderer tile, whose bounds and streams
+// replace sb / tb / xy / rgbw; its finished pixels go to the tile's own FilmTilePixel buffer instead of the film.
+template <int H, int TW, bool FMA, bool TILES = false>
+__global__ void __launch_bounds__(TW, TILES ? 1 : PBRT_CLASS_RESIDENT_THREADS / TW) splat_class_kernel(ClassParams CP) {
     typedef ClassCfg<H> C;
     constexpr int ROWS = C::ROWS, LIVE = C::LIVE, K = C::K, COLB = C::COLB, BLK = C::BLK;
     constexpr int NPX = ClassSmem<H, TW>::NPX;
     const SplatParams &P = CP.S;
     extern __shared__ __align__(16) unsigned char smem[];
     const int tid = threadIdx.x;
+    Bounds sb = P.sb, tb = P.tb;
+    const float2 *sxy = CP.S.xy;
+    const float4 *srgbw = CP.S.rgbw;
+    float4 *tile_out = nullptr;
+    if (TILES) {
+        const SplatTile t = P.tiles[blockIdx.z];
+        sb = t.sb;
+        tb = t.tb;
+        sxy += t.sample_offset;
+        srgbw += t.sample_offset;
+        tile_out = P.tile_out + t.pixel_offset;
+        if (tb.x1 <= tb.x0 || tb.y1 <= tb.y0 || sb.x1 <= sb.x0 || sb.y1 <= sb.y0) return;
+        if (tb.x0 + (int)blockIdx.x * TW >= tb.x1) return;  // the grid is sized for the widest tile
+    }
     // Programmatic dependent launch: the next splat launch of the stream may fill the SM slots this grid's early finishers
     // leave (the grid is one wave, its tail would idle otherwise).  Nothing a splat launch reads before its first flush
     // is written by the splat launch ahead of it; the film is, so its first access waits for that grid (film_wait).
@@ -452,19 +468,19 @@ __global__ void __launch_bounds__(TW, PBRT_CLASS_RESIDENT_THREADS / TW) splat_cl
     const unsigned a_rec = sbase + CP.blob_bytes + ClassSmem<H, TW>::MASK_BYTES;
     const unsigned a_flag = a_rec + (unsigned)(NPX * pitch) * 16u;
 
-    const int cx0 = P.tb.x0 + blockIdx.x * TW;              // first output column of the strip
-    const int cy0 = CP.seg_start[blockIdx.y];  // first output row
-    const int cy1 = CP.seg_start[blockIdx.y + 1];
+    const int cx0 = tb.x0 + blockIdx.x * TW;              // first output column of the strip
+    const int cy0 = TILES ? tb.y0 : CP.seg_start[blockIdx.y];  // first output row
+    const int cy1 = TILES ? tb.y1 : CP.seg_start[blockIdx.y + 1];
     const int x = cx0 + tid;
-    const bool col_ok = x < P.tb.x1;
+    const bool col_ok = x < tb.x1;
     const float fx = (float)x;
-    const int W = P.sb.x1 - P.sb.x0;
+    const int W = sb.x1 - sb.x0;
     const bool clamp_on = P.max_lum < __int_as_float(0x7f800000);
     const float rH = (float)H;                 // == P.rx == P.ry
     const float c16 = (1.f / rH) * 16.f;       // inv_radius * 16, exact
 
     // staged nominal pixels of a row: [sx0, sx1); local index = nx - (cx0 - H)
-    const int sx0 = max(cx0 - H, P.sb.x0), sx1 = min(cx0 + TW + H, P.sb.x1);
+    const int sx0 = max(cx0 - H, sb.x0), sx1 = min(cx0 + TW + H, sb.x1);
     const int nstaged = max(sx1 - sx0, 0) * spp;
     // element e = tid + k*TW of the staged run is sample `sidx` of staged pixel q: advance (q, sidx) without dividing
     const int q0 = tid / spp, r0 = tid - q0 * spp;
@@ -509,7 +525,7 @@ __global__ void __launch_bounds__(TW, PBRT_CLASS_RESIDENT_THREADS / TW) splat_cl
     };
 
     for (int ny = cy0 - H; ny < cy1 + H; ++ny) {
-        const bool row_has_samples = ny >= P.sb.y0 && ny < P.sb.y1 && nstaged > 0;
+        const bool row_has_samples = ny >= sb.y0 && ny < sb.y1 && nstaged > 0;
         // the film pixel this row's flush adds to: loaded ahead of the gather, which hides the latency
         const int yo = ny - H;
         const bool flush = col_ok && yo >= cy0 && yo < cy1;
@@ -518,9 +534,9 @@ __global__ void __launch_bounds__(TW, PBRT_CLASS_RESIDENT_THREADS / TW) splat_cl
         if (row_has_samples) {
             __syncthreads();  // previous row fully consumed
             // ---------------- pre-pass: one thread per sample of the row ----------------
-            const size_t row_base = ((size_t)(ny - P.sb.y0) * W + (sx0 - P.sb.x0)) * (size_t)spp;
-            const float2 *gxy = P.xy + row_base;
-            const float4 *grgbw = P.rgbw + row_base;
+            const size_t row_base = ((size_t)(ny - sb.y0) * W + (sx0 - sb.x0)) * (size_t)spp;
+            const float2 *gxy = sxy + row_base;
+            const float4 *grgbw = srgbw + row_base;
             const float fny = (float)ny, fnyH = fny + rH, fnyh = fny + 0.5f;
             const bool near_y = ny < 3, check_y = !near_y && __clz(ny) != __clz(ny + H);
             int sidx = r0;
@@ -683,7 +699,7 @@ __global__ void __launch_bounds__(TW, PBRT_CLASS_RESIDENT_THREADS / TW) splat_cl
             if (tid < 8) s_mask[(parity ^ 1) * 8 + tid] = 0u;  // last read before this row's first barrier
             // pull the next sample row of this strip into L2 while this one is gathered
 #ifndef PBRT_NO_PREFETCH
-            if (tid == 0 && ny + 1 < P.sb.y1 && ny + 1 < cy1 + H) {
+            if (tid == 0 && ny + 1 < sb.y1 && ny + 1 < cy1 + H) {
                 // one bulk prefetch per stream, in whole 16-byte granules inside the run
                 const size_t bxy = reinterpret_cast<size_t>(gxy + (size_t)W * spp);
                 const size_t nxy = (bxy + 15) & ~(size_t)15;
@@ -692,7 +708,7 @@ __global__ void __launch_bounds__(TW, PBRT_CLASS_RESIDENT_THREADS / TW) splat_cl
                 asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(nrgbw), "r"((unsigned)(nstaged * 16)) : "memory");
             }
 #endif
-            if (flush) {
+            if (flush && !TILES) {
                 if (!film_ready) { asm volatile("griddepcontrol.wait;" ::: "memory"); film_ready = true; }
                 px = P.film[fo];
             }
@@ -723,7 +739,7 @@ __global__ void __launch_bounds__(TW, PBRT_CLASS_RESIDENT_THREADS / TW) splat_cl
 #pragma unroll 1
                 for (int d = -H; d <= H; ++d) {
                     const int nx = x + d;
-                    if (nx < P.sb.x0 || nx >= P.sb.x1) continue;
+                    if (nx < sb.x0 || nx >= sb.x1) continue;
                     const int pl = nx - (cx0 - H);
                     const float4 *pa = s_rec + pl * pitch;
                     const unsigned char *pf = s_flag + pl * pitch;
@@ -862,8 +878,8 @@ __global__ void __launch_bounds__(TW, PBRT_CLASS_RESIDENT_THREADS / TW) splat_cl
                         const unsigned fl = pf[s] & 15u;
                         if (fl == CF_SLOW) {
                             // no class: the CPU path's expressions for this (sample, column)
-                            const size_t index = ((size_t)(ny - P.sb.y0) * (P.sb.x1 - P.sb.x0) + (nx - P.sb.x0)) * (size_t)spp + c0 + s;
-                            const SlowWeights<ROWS> sw = class_slow_weights<H>(P.xy, P.table, index, nx, ny, x, P.rx, P.ry);
+                            const size_t index = ((size_t)(ny - sb.y0) * (sb.x1 - sb.x0) + (nx - sb.x0)) * (size_t)spp + c0 + s;
+                            const SlowWeights<ROWS> sw = class_slow_weights<H>(sxy, P.table, index, nx, ny, x, P.rx, P.ry);
                             if (sw.out_of_pixel) errbits |= ERRBIT_NOT_PIXEL_MAJOR;
 #pragma unroll
                             for (int j = 0; j < ROWS; ++j) tap(j, a.x, a.y, a.z, sw.w[j]);
@@ -919,14 +935,18 @@ __global__ void __launch_bounds__(TW, PBRT_CLASS_RESIDENT_THREADS / TW) splat_cl
             // non-finite radiance (a contract violation) shows in the sums: 0 * x is NaN for x = inf or NaN
             const float z = r * 0.f + g * 0.f + b * 0.f + w * 0.f;
             if (z != z) errbits |= ERRBIT_NONFINITE;
-            if (!row_has_samples) {
-                if (!film_ready) { asm volatile("griddepcontrol.wait;" ::: "memory"); film_ready = true; }
-                px = P.film[fo];
+            if (TILES) {  // FilmTilePixel {contrib_sum, filter_weight_sum} of this tile (film.rs:39-42)
+                tile_out[(size_t)(yo - tb.y0) * (tb.x1 - tb.x0) + (x - tb.x0)] = make_float4(r, g, b, w);
+            } else {
+                if (!row_has_samples) {
+                    if (!film_ready) { asm volatile("griddepcontrol.wait;" ::: "memory"); film_ready = true; }
+                    px = P.film[fo];
+                }
+                float X, Y, Z;
+                rgb_to_xyz(r, g, b, X, Y, Z);
+                px.x += X; px.y += Y; px.z += Z; px.w += w;
+                P.film[fo] = px;
             }
-            float X, Y, Z;
-            rgb_to_xyz(r, g, b, X, Y, Z);
-            px.x += X; px.y += Y; px.z += Z; px.w += w;
-            P.film[fo] = px;
         }
 #pragma unroll
         for (int j = 0; j + 1 < ROWS; ++j) acc.move(j, j + 1);
@@ -1108,6 +1128,57 @@ static int class_pick_width(const ClassParams &CP) {
     if (fit128) return launch_class<H, 128, FMA>(CP);
     if (fit64) return launch_class<H, 64, FMA>(CP);
     return launch_class<H, 32, FMA>(CP);
+#endif
+}
+
+// Batched tiles (pbrt_film_add_samples_tiles): 32-column strips (a renderer tile of 16x16 samples is 20 pixels wide
+// at radius 2), one CTA column per tile walking the whole tile height, blockIdx.z = tile.  Launched without the
+// programmatic attribute: the kernel ahead may be the merge that still reads the tile buffers this one overwrites.
+template <int H, bool FMA>
+static int launch_class_tiles(const ClassParams &CP0, int ntiles, int max_w) {
+    constexpr int TW = 32;
+    ClassParams CP = CP0;
+    const size_t smem = ClassSmem<H, TW>::bytes(CP.blob_bytes, CP.S.spp);
+    if (smem > 227 * 1024) return -1;
+    static int attr_device = -1;
+    if (attr_device != ctx().device) {
+        PB_CUDA(cudaFuncSetAttribute(splat_class_kernel<H, TW, FMA, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_device = ctx().device;
+    }
+    CP.seg_start = nullptr;
+    CP.wait_first = 0;
+#ifdef PBRT_CLASS_TRACE
+    CP.trace = nullptr;
+#endif
+    for (int z0 = 0; z0 < ntiles; z0 += 65535) {
+        const int nz = std::min(65535, ntiles - z0);
+        ClassParams Q = CP;
+        Q.S.tiles = CP.S.tiles + z0;
+        dim3 grid((max_w + TW - 1) / TW, 1, nz);
+        splat_class_kernel<H, TW, FMA, true><<<grid, TW, smem, ctx().stream>>>(Q);
+        PB_LAUNCH_CHECK("splat_class_kernel(batched)");
+    }
+    return PBRT_OK;
+}
+
+int launch_splat_class_tiles(PbrtFilm *f, const SplatParams &P, int ntiles, int max_w, int mode) {
+    if (!f->class_bytes || !P.tiles || class_env_int("PBRT_B200_NO_CLASS", 0)) return -1;
+    if (mode != PBRT_SPLAT_EXACT && mode != PBRT_SPLAT_FMA) return -1;
+    if (P.spp > 32 || 32 % P.spp != 0) return -1;  // the uniform path needs spp to divide the strip width
+    ClassGeom g;
+    if (!class_geom(P.rx, P.ry, &g) || g.H != f->class_h) return -1;
+    ClassParams CP;
+    CP.S = P;
+    CP.blob = reinterpret_cast<const uint4 *>(f->d_class);
+    CP.blob_bytes = f->class_bytes;
+    CP.rowp = g.ROWP;
+    CP.eoff = g.EOFF;
+#ifdef PBRT_CLASS_PROBE
+    return -1;
+#else
+    const bool fma = mode == PBRT_SPLAT_FMA;
+    if (g.H == 2) return fma ? launch_class_tiles<2, true>(CP, ntiles, max_w) : launch_class_tiles<2, false>(CP, ntiles, max_w);
+    return fma ? launch_class_tiles<4, true>(CP, ntiles, max_w) : launch_class_tiles<4, false>(CP, ntiles, max_w);
 #endif
 }
 
