@@ -397,7 +397,7 @@ __device__ __noinline__ SlowWeights<2 * H + 1> class_slow_weights(const float2 *
 template <int H, int TW>
 struct ClassSmem {
     static constexpr int NPX = TW + 2 * H;
-    static constexpr int MASK_BYTES = 64;  // 2 parities x 6 words, padded
+    static constexpr int MASK_BYTES = 128;  // 2 parities x 8 masks of up to 64 bits
     __host__ __device__ static int pitch(int spp) { return spp | 1; }
     __host__ __device__ static size_t bytes(int blob_bytes, int spp) {
         return (size_t)blob_bytes + MASK_BYTES + ((size_t)NPX * pitch(spp) * 17 + 15) / 16 * 16;
@@ -421,8 +421,16 @@ constexpr int kClassUnroll4 = PBRT_CLASS_UNROLL4;  // h = 4 (twice the taps per 
 #endif
 // TILES: the batched form (pbrt_film_add_samples_tiles): blockIdx.z selects a renderer tile, whose bounds and streams
 // replace sb / tb / xy / rgbw; its finished pixels go to the tile's own FilmTilePixel buffer instead of the film.
-template <int H, int TW, bool FMA, bool TILES = false>
+// WIDE: 64-bit per-index masks (33..64 samples per pixel); the 32-bit form is the tuned one and stays as it is.
+__device__ __forceinline__ int mask_popc(unsigned m) { return __popc(m); }
+__device__ __forceinline__ int mask_popc(u64 m) { return __popcll(m); }
+__device__ __forceinline__ int mask_ffs(unsigned m) { return __ffs((int)m); }
+__device__ __forceinline__ int mask_ffs(u64 m) { return __ffsll((long long)m); }
+
+template <int H, int TW, bool FMA, bool TILES = false, bool WIDE = false>
 __global__ void __launch_bounds__(TW, TILES ? 1 : PBRT_CLASS_RESIDENT_THREADS / TW) splat_class_kernel(ClassParams CP) {
+    typedef typename std::conditional<WIDE, u64, unsigned>::type M;  // one bit per sample index of a pixel
+    constexpr int MB = WIDE ? 64 : 32;
     typedef ClassCfg<H> C;
     constexpr int ROWS = C::ROWS, LIVE = C::LIVE, K = C::K, COLB = C::COLB, BLK = C::BLK;
     constexpr int NPX = ClassSmem<H, TW>::NPX;
@@ -455,12 +463,12 @@ __global__ void __launch_bounds__(TW, TILES ? 1 : PBRT_CLASS_RESIDENT_THREADS / 
 #endif
     const int spp = P.spp;
     const int pitch = ClassSmem<H, TW>::pitch(spp);
-    unsigned *s_mask = reinterpret_cast<unsigned *>(smem + CP.blob_bytes);
+    M *s_mask = reinterpret_cast<M *>(smem + CP.blob_bytes);
     float4 *s_rec = reinterpret_cast<float4 *>(smem + CP.blob_bytes + ClassSmem<H, TW>::MASK_BYTES);
     unsigned char *s_flag = reinterpret_cast<unsigned char *>(s_rec + (size_t)NPX * pitch);
 
     for (int i = tid; i < CP.blob_bytes / 16; i += TW) reinterpret_cast<uint4 *>(smem)[i] = CP.blob[i];
-    if (tid < ClassSmem<H, TW>::MASK_BYTES / 4) s_mask[tid] = 0u;
+    if (tid < 16) s_mask[tid] = M(0);
     __syncthreads();
     // shared-window address of the blob, kept opaque so that it lives in a register
     unsigned sbase = (unsigned)__cvta_generic_to_shared(smem);
@@ -490,8 +498,8 @@ __global__ void __launch_bounds__(TW, TILES ? 1 : PBRT_CLASS_RESIDENT_THREADS / 
     const float fdq = (float)dq;
     // a thread keeps its sample index for the whole row when spp divides the strip width: the per-index class masks
     // are then reduced in registers; otherwise (and above 32 spp) every sample takes the general body
-    const bool mask_mode = dr == 0 && spp <= 32;
-    const unsigned sppmask = spp >= 32 ? 0xffffffffu : ((1u << spp) - 1u);
+    const bool mask_mode = dr == 0 && spp <= MB;
+    const M sppmask = spp >= MB ? ~M(0) : ((M(1) << spp) - M(1));
     constexpr int U = PBRT_CLASS_PREPASS_BATCH;
     // Which of this thread's batches need more than the plain classification.  The pixels of batch k are the same in
     // every row, so both are found once, bit k per batch:
@@ -683,9 +691,9 @@ __global__ void __launch_bounds__(TW, TILES ? 1 : PBRT_CLASS_RESIDENT_THREADS / 
             // column on the left / right.  Words: 0 !up 1 !down 2 !left-all 3 !left-none 4 !right-all 5 !right-none
             // 6 some sample may have phase 0 on y (its extra tap follows the run it is in)  7 ... on x (it reaches both
             // outermost columns: taken per lane among the uniform samples of an edge-column visit)
-            unsigned *mk = s_mask + parity * 8;
+            M *mk = s_mask + parity * 8;
             if (mask_mode && tid < nstaged) {
-                const unsigned bit = 1u << r0;
+                const M bit = M(1) << r0;
                 if (!(andf & CF_UP)) atomicOr(&mk[0], bit);
                 if (!(andf & CF_DOWN)) atomicOr(&mk[1], bit);
                 if ((orf & CF_BOTH) == CF_BOTH) atomicOr(&mk[6], bit);
@@ -696,7 +704,7 @@ __global__ void __launch_bounds__(TW, TILES ? 1 : PBRT_CLASS_RESIDENT_THREADS / 
                 if (orf & CF_RIGHT) atomicOr(&mk[5], bit);
             }
             __syncthreads();
-            if (tid < 8) s_mask[(parity ^ 1) * 8 + tid] = 0u;  // last read before this row's first barrier
+            if (tid < 8) s_mask[(parity ^ 1) * 8 + tid] = M(0);  // last read before this row's first barrier
             // pull the next sample row of this strip into L2 while this one is gathered
 #ifndef PBRT_NO_PREFETCH
             if (tid == 0 && ny + 1 < sb.y1 && ny + 1 < cy1 + H) {
@@ -718,15 +726,15 @@ __global__ void __launch_bounds__(TW, TILES ? 1 : PBRT_CLASS_RESIDENT_THREADS / 
 #else
             if (col_ok) {
 #endif
-                const unsigned m_up = mask_mode ? ~mk[0] & sppmask : 0u, m_down = mask_mode ? ~mk[1] & sppmask : 0u;
-                const unsigned m_lall = ~mk[2] & sppmask, m_lnone = mask_mode ? ~mk[3] & sppmask : 0u;
-                const unsigned m_rall = ~mk[4] & sppmask, m_rnone = mask_mode ? ~mk[5] & sppmask : 0u;
-                const unsigned m_both = mk[6] & sppmask, m_xboth = mk[7] & sppmask;
+                const M m_up = mask_mode ? ~mk[0] & sppmask : M(0), m_down = mask_mode ? ~mk[1] & sppmask : M(0);
+                const M m_lall = ~mk[2] & sppmask, m_lnone = mask_mode ? ~mk[3] & sppmask : M(0);
+                const M m_rall = ~mk[4] & sppmask, m_rnone = mask_mode ? ~mk[5] & sppmask : M(0);
+                const M m_both = mk[6] & sppmask, m_xboth = mk[7] & sppmask;
                 // A "simple" row (every stratified row without a phase-0 or classless sample): sample indices 0..n_up-1 are
                 // "up" everywhere in the strip, the rest "down", and each index either always or never reaches an
                 // outermost column.  Its visits are two loops with no per-sample decisions.
-                const int n_up = __popc(m_up);
-                const bool simple_rows = mask_mode && m_up == ((1u << n_up) - 1u) && (m_up | m_down) == sppmask;
+                const int n_up = mask_popc(m_up);
+                const bool simple_rows = mask_mode && m_up == ((M(1) << n_up) - M(1)) && (m_up | m_down) == sppmask;
                 // outermost columns: every index reaches its left one throughout, or its right one throughout (a sample on
                 // x phase 0 reaches both and fits either)
                 const bool simple_edges = (m_lall | m_rall) == sppmask;
@@ -746,7 +754,7 @@ __global__ void __launch_bounds__(TW, TILES ? 1 : PBRT_CLASS_RESIDENT_THREADS / 
                     // shared-window address of this column inside the block at offset 0
                     const unsigned qcol = sbase + (unsigned)((H - d) * COLB);
                     const bool interior = d != -H && d != H;
-                    unsigned run_up = m_up, run_down = m_down, live = sppmask;
+                    M run_up = m_up, run_down = m_down, live = sppmask;
                     if (d == -H) { run_up &= m_rall; run_down &= m_rall; live &= ~m_rnone; }
                     if (d == H) { run_up &= m_lall; run_down &= m_lall; live &= ~m_lnone; }
                     // taps I0..I1-1 of one sample against this column: DOWN = false: tap i is window row i, weights in
@@ -791,42 +799,42 @@ __global__ void __launch_bounds__(TW, TILES ? 1 : PBRT_CLASS_RESIDENT_THREADS / 
                     // the samples whose bits are set; those of `lane` per lane: only a sample that itself reaches this
                     // outermost column (x phase 0 among samples that reach the other one)
                     const unsigned reach = d == -H ? CF_RIGHT : (d == H ? CF_LEFT : 0u);
-                    auto run_bits = [&](unsigned bits, auto down_tag, auto i0_tag, auto i1_tag) {
+                    auto run_bits = [&](M bits, auto down_tag, auto i0_tag, auto i1_tag) {
                         if (decltype(i0_tag)::value >= decltype(i1_tag)::value) return;
                         while (bits) {  // two at a time where neighbours are set (stratified streams: always)
-                            const int s0 = __ffs((int)bits) - 1;
-                            const unsigned two = 3u << s0;
+                            const int s0 = mask_ffs(bits) - 1;
+                            const M two = M(3) << s0;
                             if ((bits & two) == two) {
                                 const float4 a0 = pa[s0], a1 = pa[s0 + 1];
                                 bits &= ~two;
                                 body(a0, down_tag, i0_tag, i1_tag);
                                 body(a1, down_tag, i0_tag, i1_tag);
                             } else {
-                                bits &= bits - 1;
+                                bits &= bits - M(1);
                                 body(pa[s0], down_tag, i0_tag, i1_tag);
                             }
                         }
                     };
                     // the same with some indices (`lane`) taken per lane (rows that hold an x phase-0 sample)
-                    auto run_bits_lane = [&](unsigned bits, const unsigned lane, auto down_tag, auto i0_tag, auto i1_tag) {
+                    auto run_bits_lane = [&](M bits, const M lane, auto down_tag, auto i0_tag, auto i1_tag) {
                         if (decltype(i0_tag)::value >= decltype(i1_tag)::value) return;
                         while (bits) {
-                            const int s0 = __ffs((int)bits) - 1;
-                            bits &= bits - 1;
-                            if (!((lane >> s0) & 1u) || (pf[s0] & reach)) body(pa[s0], down_tag, i0_tag, i1_tag);
+                            const int s0 = mask_ffs(bits) - 1;
+                            bits &= bits - M(1);
+                            if (!((lane >> s0) & M(1)) || (pf[s0] & reach)) body(pa[s0], down_tag, i0_tag, i1_tag);
                         }
                     };
                     if (simple_rows && (interior || simple_edges)) {
                         // up-run with taps [U0, U1), then down-run with taps [D0, D1).  A phase-0 sample runs as the kind of
                         // its index; its one further tap keeps the stream's order per pixel: window row 2h (which only
                         // "down" samples touch otherwise) right after the up-run, row 0 (only "up" samples) after it too.
-                        const unsigned uni = d == -H ? m_rall : m_lall;             // edge column: every sample of the index reaches it
-                        const unsigned lane = interior ? 0u : m_xboth & ~uni;        // ... only samples on x phase 0 do
-                        const unsigned eb_all = m_both & (interior ? sppmask : (uni | lane));
-                        auto extras = [&](unsigned eb, const int row) {
+                        const M uni = d == -H ? m_rall : m_lall;             // edge column: every sample of the index reaches it
+                        const M lane = interior ? M(0) : m_xboth & ~uni;        // ... only samples on x phase 0 do
+                        const M eb_all = m_both & (interior ? sppmask : (uni | lane));
+                        auto extras = [&](M eb, const int row) {
                             while (eb) {
-                                const int s0 = __ffs((int)eb) - 1;
-                                eb &= eb - 1;
+                                const int s0 = mask_ffs(eb) - 1;
+                                eb &= eb - M(1);
                                 const unsigned fl = pf[s0];
                                 if ((fl & CF_BOTH) == CF_BOTH && (fl & reach) == reach) extra_tap(pa[s0], row);
                             }
@@ -895,31 +903,31 @@ __global__ void __launch_bounds__(TW, TILES ? 1 : PBRT_CLASS_RESIDENT_THREADS / 
                         }
                     };
                     // one segment: a run of consecutive indices (always, at an interior column) or scattered ones
-                    auto segment = [&](const unsigned seg, auto down_tag) {
-                        const int first = __ffs((int)seg) - 1;
-                        const unsigned shifted = seg >> first;
-                        if ((shifted & (shifted + 1u)) == 0u) run(pa + first, __popc(seg), down_tag, I_0{}, I_LIVE{});
+                    auto segment = [&](const M seg, auto down_tag) {
+                        const int first = mask_ffs(seg) - 1;
+                        const M shifted = seg >> first;
+                        if ((shifted & (shifted + M(1))) == M(0)) run(pa + first, mask_popc(seg), down_tag, I_0{}, I_LIVE{});
                         else run_bits(seg, down_tag, I_0{}, I_LIVE{});
                     };
                     // Any other row: the live samples in stream order, cut into segments of one kind.  Skipped samples do
                     // not end a segment.  Sample indices go in chunks of 32 (the masks describe the first chunk; above 32
                     // spp every sample is general).
-                    for (int c0 = 0; c0 < spp; c0 += 32, pa += 32, pf += 32) {
-                        unsigned rem = c0 == 0 ? live : (spp - c0 >= 32 ? 0xffffffffu : (1u << (spp - c0)) - 1u);
+                    for (int c0 = 0; c0 < spp; c0 += MB, pa += MB, pf += MB) {
+                        M rem = c0 == 0 ? live : (spp - c0 >= MB ? ~M(0) : (M(1) << (spp - c0)) - M(1));
                         while (rem) {
-                            const unsigned low = rem & (0u - rem);
+                            const M low = rem & (M(0) - rem);
                             if (low & run_up) {
-                                const unsigned nb = rem & ~run_up;  // live samples that are not "up": the first one ends the segment
-                                const unsigned seg = nb ? rem & ((nb & (0u - nb)) - 1u) : rem;
+                                const M nb = rem & ~run_up;  // live samples that are not "up": the first one ends the segment
+                                const M seg = nb ? rem & ((nb & (M(0) - nb)) - M(1)) : rem;
                                 segment(seg, std::false_type{});
                                 rem &= ~seg;
                             } else if (low & run_down) {
-                                const unsigned nb = rem & ~run_down;
-                                const unsigned seg = nb ? rem & ((nb & (0u - nb)) - 1u) : rem;
+                                const M nb = rem & ~run_down;
+                                const M seg = nb ? rem & ((nb & (M(0) - nb)) - M(1)) : rem;
                                 segment(seg, std::true_type{});
                                 rem &= ~seg;
                             } else {
-                                general(__ffs((int)low) - 1, c0);
+                                general(mask_ffs(low) - 1, c0);
                                 rem &= ~low;
                             }
                         }
@@ -1050,7 +1058,7 @@ static cudaError_t class_segments(int y0, int rows, int cols, int segs, int per_
     return cudaSuccess;
 }
 
-template <int H, int TW, bool FMA>
+template <int H, int TW, bool FMA, bool WIDE = false>
 static int launch_class(const ClassParams &CP0) {
     ClassParams CP = CP0;
     SplatParams &P = CP.S;
@@ -1058,11 +1066,11 @@ static int launch_class(const ClassParams &CP0) {
     if (smem > 227 * 1024) return -1;
     static int attr_device = -1;
     if (attr_device != ctx().device) {
-        PB_CUDA(cudaFuncSetAttribute(splat_class_kernel<H, TW, FMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        PB_CUDA(cudaFuncSetAttribute(splat_class_kernel<H, TW, FMA, false, WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_device = ctx().device;
     }
     int per_sm = 0;
-    PB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, splat_class_kernel<H, TW, FMA>, TW, smem));
+    PB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, splat_class_kernel<H, TW, FMA, false, WIDE>, TW, smem));
     if (per_sm < 1) return -1;
     const int cols = (bw(P.tb) + TW - 1) / TW;
     const int rows = bh(P.tb);
@@ -1100,7 +1108,7 @@ static int launch_class(const ClassParams &CP0) {
     attr[0].val.programmaticStreamSerializationAllowed = class_env_int("PBRT_B200_NO_PDL", 0) ? 0 : 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    PB_CUDA(cudaLaunchKernelEx(&cfg, splat_class_kernel<H, TW, FMA>, CP));
+    PB_CUDA(cudaLaunchKernelEx(&cfg, splat_class_kernel<H, TW, FMA, false, WIDE>, CP));
     PB_LAUNCH_CHECK("splat_class_kernel");
     last_launch = ctx().launches;  // the library launched nothing else since, if this still equals ctx().launches next time
     return PBRT_OK;
@@ -1117,6 +1125,14 @@ static int class_pick_width(const ClassParams &CP) {
     if (force == 64) return launch_class<H, 64, FMA>(CP);
     if (force == 32) return launch_class<H, 32, FMA>(CP);
     const int spp = CP.S.spp;
+    if (spp > 32) {
+        // 33..64 spp: 64-bit index masks, and only the shapes that run on the uniform path (spp divides the strip and
+        // two CTAs fit an SM: 64 spp on 64 columns, 48 on 96) — two warps per CTA, four per SM; anything else is
+        // better off with the window kernel
+        if (64 % spp == 0 && ClassSmem<H, 64>::bytes(CP.blob_bytes, spp) * 2 <= 226 * 1024) return launch_class<H, 64, FMA, true>(CP);
+        if (96 % spp == 0 && ClassSmem<H, 96>::bytes(CP.blob_bytes, spp) * 2 <= 226 * 1024) return launch_class<H, 96, FMA, true>(CP);
+        return -1;
+    }
     // widest strip of which two CTAs fit an SM — among the widths spp divides, if any: a thread then keeps its sample
     // index along a row and the row can run on the uniform path (24 spp: 96 columns 2.2 x the rate of 128)
     const bool fit128 = ClassSmem<H, 128>::bytes(CP.blob_bytes, spp) * 2 <= 226 * 1024;
@@ -1185,8 +1201,10 @@ int launch_splat_class_tiles(PbrtFilm *f, const SplatParams &P, int ntiles, int 
 int launch_splat_class(PbrtFilm *f, const SplatParams &P, int mode) {
     if (!f->class_bytes || P.tiles || class_env_int("PBRT_B200_NO_CLASS", 0)) return -1;
     if (mode != PBRT_SPLAT_EXACT && mode != PBRT_SPLAT_FMA) return -1;
-    // the per-index class masks cover 32 sample indices; longer pixel runs keep the window kernel's narrower strips
-    if (P.spp > 32 && !class_env_int("PBRT_B200_CLASS_ANY_SPP", 0)) return -1;
+    // the per-index class masks cover 64 sample indices; longer pixel runs keep the window kernel's narrower strips
+    // (33..64 spp with 64-bit masks is built and tested but measured slower than the window kernel — two CTAs of two
+    // warps per SM: 3.0e10 against 3.4e10 samples/s at 64 spp — so it runs only on request)
+    if (P.spp > 64 || (P.spp > 32 && !class_env_int("PBRT_B200_WIDE", 0))) return -1;
     ClassGeom g;
     if (!class_geom(P.rx, P.ry, &g) || g.H != f->class_h) return -1;
     ClassParams CP;

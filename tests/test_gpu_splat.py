@@ -135,10 +135,13 @@ def test_large_spp_uses_narrower_strips_exact(gpu, orc, spp):
 
 
 @pytest.mark.parametrize("name", ["gaussian", "lanczos"])
-@pytest.mark.parametrize("spp", [1, 3, 6, 12, 20, 24, 32])
-def test_samples_per_pixel_the_strip_width_is_chosen_for(gpu, orc, name, spp):
+@pytest.mark.parametrize("spp", [1, 3, 6, 12, 20, 24, 32, 48, 64])
+def test_samples_per_pixel_the_strip_width_is_chosen_for(gpu, orc, monkeypatch, name, spp):
     """The class kernel picks 128 / 96 / 64 columns so that spp divides the strip (a thread keeps its sample index:
-    uniform path) and otherwise runs every sample per lane: 1..32 spp at radius 2 and 4, a film wider than two strips."""
+    uniform path) and otherwise runs every sample per lane: 1..32 spp at radius 2 and 4, a film wider than two strips;
+    48 and 64 spp with 64-bit index masks on 96 / 64 columns (PBRT_B200_WIDE=1; off by default: the window kernel is
+    faster there)."""
+    monkeypatch.setenv("PBRT_B200_WIDE", "1")
     film, of = run_pair(gpu, orc, name, (300, 21), [0, 0, 1, 1], (-2, -2, 302, 23), spp, gpu.SPLAT_EXACT, seed=spp)
     assert np.array_equal(u32(film.read_pixels()), u32(of.pixels()))
 
