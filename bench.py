@@ -325,6 +325,42 @@ def main():
         iso[i + 1].record(stream)
     barrier()
     per_step = [iso[i].elapsed_time(iso[i + 1]) for i in range(10)]
+    # and K back-to-back launches that alternate between two sample buffers, as a renderer that generates new samples for
+    # every pass would issue them: a launch that reads other buffers than the one ahead of it waits for that grid before
+    # its first load (splat_class.cu), so only its table staging overlaps
+    alt_ms = alt_overlap_ms = None
+    if world == 1:
+        try:
+            xy_b, rgbw_b, _ = synth.samples(my_sb.as4(), spp, seed=2, index_bounds=full_sb.as4())
+            bufs = [(xy_d, rgbw_d), (xy_b, rgbw_b)]
+            for i in range(4):
+                film.add_samples_tile(sb_list, spp, *bufs[i & 1], mode)
+            barrier()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record(stream)
+            for i in range(args.steps):
+                film.add_samples_tile(sb_list, spp, *bufs[i & 1], mode)
+            a1.record(stream)
+            barrier()
+            alt_ms = a0.elapsed_time(a1) / args.steps
+            film.check()
+            # the same with pbrt_b200_overlap_passes(1): the caller vouches that a pass's samples were complete before
+            # the previous pass was issued (true here: both buffers exist since before the loop)
+            pb.overlap_passes(True)
+            for i in range(4):
+                film.add_samples_tile(sb_list, spp, *bufs[i & 1], mode)
+            barrier()
+            a0.record(stream)
+            for i in range(args.steps):
+                film.add_samples_tile(sb_list, spp, *bufs[i & 1], mode)
+            a1.record(stream)
+            barrier()
+            alt_overlap_ms = a0.elapsed_time(a1) / args.steps
+            pb.overlap_passes(False)
+            film.check()
+            del xy_b, rgbw_b, bufs
+        except Exception:
+            alt_ms = None
     t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -341,7 +377,7 @@ def main():
         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
         "traffic": measured_traffic(args.workload, args.mode) if world == 1 else None, "peak_source": peak_src,
         "kernel": "splat_atomic_kernel" if args.mode == "atomic" else ("splat_class_kernel" if wl["radius"][0] in (2.0, 4.0) and spp <= 32 else "splat_window_kernel"),
-        "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kern_ms, "kernel_ms_isolated": sum(per_step) / len(per_step),
+        "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kern_ms, "kernel_ms_isolated": sum(per_step) / len(per_step), "kernel_ms_alternating_buffers": alt_ms, "kernel_ms_alternating_buffers_overlap_passes": alt_overlap_ms,
         "note": "24 B/sample read + 32 B/film pixel RMW per launch; the splat is bound by shared-memory load latency and instruction issue, not by HBM (DESIGN.md section 5, profiles/)",
     }
 

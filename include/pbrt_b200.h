@@ -72,6 +72,12 @@ int pbrt_b200_synchronize(void);
 int pbrt_b200_device_info(int *device, int *sm_count, int *cc_major, int *cc_minor, uint64_t *hbm_bytes);
 /* kernels launched by this library since init (bench.py's gpu_launches) */
 uint64_t pbrt_b200_launch_count(void);
+/* Consecutive pixel-major splat passes overlap (the next pass starts in the SM slots the one ahead leaves and waits for
+ * it before it touches the film) when both read the same sample buffers.  on = 1 extends that to passes reading any
+ * buffers: the caller then guarantees that the samples of a pass were complete before the PREVIOUS call on the stream
+ * was issued (generated a pass ahead, or on another stream joined earlier) — a pass no longer waits for the kernel ahead
+ * of it before its first load.  Returns the previous setting; default 0. */
+int pbrt_b200_overlap_passes(int on);
 /* raw device / pinned-host buffers for callers without a CUDA runtime binding */
 int pbrt_b200_malloc(uint64_t bytes, void **dev_out);
 int pbrt_b200_free(void *dev);

@@ -11,7 +11,7 @@ from .film import FILTER_TABLE_WIDTH, SPLAT_ATOMIC, SPLAT_EXACT, SPLAT_FMA, Film
 from .filters import (BoxFilter, Filter, GaussianFilter, LanczosSincFilter, MitchellFilter, TriangleFilter,
                       make_filter)
 from .geometry import Bounds2f, Bounds2i, Point2i
-from .runtime import (DeviceBuffer, PinnedBuffer, bind_host_to_device_numa, device_info, init, launch_count, set_stream,
+from .runtime import (DeviceBuffer, PinnedBuffer, bind_host_to_device_numa, device_info, init, launch_count, overlap_passes, set_stream,
                       synchronize)
 from .textures import (ConstantTexture, SurfaceInteraction, Texture, create_constant_float_texture,
                        create_constant_spectrum_texture, weight_lut)
@@ -21,7 +21,7 @@ __all__ = [
     "SPLAT_EXACT", "SPLAT_FMA", "SPLAT_ATOMIC",
     "Filter", "BoxFilter", "TriangleFilter", "GaussianFilter", "MitchellFilter", "LanczosSincFilter", "make_filter",
     "Bounds2f", "Bounds2i", "Point2i",
-    "DeviceBuffer", "PinnedBuffer", "bind_host_to_device_numa", "device_info", "init", "launch_count", "set_stream", "synchronize",
+    "DeviceBuffer", "PinnedBuffer", "bind_host_to_device_numa", "device_info", "init", "launch_count", "overlap_passes", "set_stream", "synchronize",
     "Texture", "ConstantTexture", "SurfaceInteraction", "create_constant_float_texture",
     "create_constant_spectrum_texture", "weight_lut",
 ]

@@ -47,6 +47,7 @@ PROTOTYPES = {
     "pbrt_b200_synchronize": (C.c_int, []),
     "pbrt_b200_device_info": (C.c_int, [_i32p, _i32p, _i32p, _i32p, C.POINTER(C.c_uint64)]),
     "pbrt_b200_launch_count": (C.c_uint64, []),
+    "pbrt_b200_overlap_passes": (C.c_int, [C.c_int]),
     "pbrt_b200_malloc": (C.c_int, [C.c_uint64, _vpp]),
     "pbrt_b200_free": (C.c_int, [_vp]),
     "pbrt_b200_host_alloc": (C.c_int, [C.c_uint64, _vpp]),

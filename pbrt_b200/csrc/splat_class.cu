@@ -1058,6 +1058,8 @@ static cudaError_t class_segments(int y0, int rows, int cols, int segs, int per_
     return cudaSuccess;
 }
 
+static int g_overlap_any = 0;  // pbrt_b200_overlap_passes
+
 template <int H, int TW, bool FMA, bool WIDE = false>
 static int launch_class(const ClassParams &CP0) {
     ClassParams CP = CP0;
@@ -1094,7 +1096,7 @@ static int launch_class(const ClassParams &CP0) {
     // render over resident samples); any other launch waits first and overlaps only its table staging.
     static const void *last_xy = nullptr, *last_rgbw = nullptr;
     static uint64_t last_launch = ~0ull;
-    CP.wait_first = !(last_xy == P.xy && last_rgbw == P.rgbw && last_launch == ctx().launches && !P.tiles) ||
+    CP.wait_first = !((g_overlap_any || (last_xy == P.xy && last_rgbw == P.rgbw)) && last_launch == ctx().launches && !P.tiles) ||
                     class_env_int("PBRT_B200_PDL_WAIT_FIRST", 0);
     last_xy = P.xy;
     last_rgbw = P.rgbw;
@@ -1105,7 +1107,10 @@ static int launch_class(const ClassParams &CP0) {
     cfg.stream = ctx().stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = class_env_int("PBRT_B200_NO_PDL", 0) ? 0 : 1;
+    // (a launch that must wait before its first load gains nothing from starting early — its CTAs would only hold SM
+    // slots the grid ahead still needs: 0.366 ms per pass against 0.350 ms — so it is launched the ordinary way)
+    attr[0].val.programmaticStreamSerializationAllowed =
+        (class_env_int("PBRT_B200_NO_PDL", 0) || (CP.wait_first && !class_env_int("PBRT_B200_PDL_WAIT_FIRST", 0))) ? 0 : 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     PB_CUDA(cudaLaunchKernelEx(&cfg, splat_class_kernel<H, TW, FMA, false, WIDE>, CP));
@@ -1261,4 +1266,11 @@ extern "C" int pbrt_b200_debug_class_segments(int y0, int rows, int cols, int se
     pb::class_segment_rows(y0, rows, cols, segs, per_sm, h, nsm, &v);
     for (int i = 0; i <= segs; ++i) out[i] = v[i];
     return segs + 1;
+}
+
+// [UTIL] include/pbrt_b200.h
+extern "C" int pbrt_b200_overlap_passes(int on) {
+    const int was = pb::g_overlap_any;
+    pb::g_overlap_any = on ? 1 : 0;
+    return was;
 }

@@ -67,6 +67,12 @@ def launch_count() -> int:
     return int(_lib.lib.pbrt_b200_launch_count())
 
 
+def overlap_passes(on: bool) -> bool:
+    """Let consecutive splat passes overlap whatever buffers they read (include/pbrt_b200.h: the caller guarantees the
+    samples of a pass were complete before the previous call on the stream was issued).  Returns the previous setting."""
+    return bool(_lib.lib.pbrt_b200_overlap_passes(1 if on else 0))
+
+
 def device_info() -> dict:
     dev, sm, maj, mnr = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
     mem = C.c_uint64()

@@ -106,6 +106,7 @@ extern "C" {
     pub fn pbrt_b200_synchronize() -> c_int;
     pub fn pbrt_b200_device_info(device: *mut c_int, sm_count: *mut c_int, cc_major: *mut c_int, cc_minor: *mut c_int, hbm_bytes: *mut u64) -> c_int;
     pub fn pbrt_b200_launch_count() -> u64;
+    pub fn pbrt_b200_overlap_passes(on: c_int) -> c_int;
     pub fn pbrt_b200_malloc(bytes: u64, dev_out: *mut *mut c_void) -> c_int;
     pub fn pbrt_b200_free(dev: *mut c_void) -> c_int;
     pub fn pbrt_b200_host_alloc(bytes: u64, host_out: *mut *mut c_void) -> c_int;

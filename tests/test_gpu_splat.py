@@ -347,6 +347,28 @@ def test_back_to_back_passes_overlap_without_changing_a_bit(gpu, orc, monkeypatc
     assert np.array_equal(u32(got), u32(of.pixels()))
 
 
+def test_overlap_passes_over_alternating_buffers_changes_no_bit(gpu, orc):
+    """pbrt_b200_overlap_passes(1): consecutive passes overlap although they read different sample buffers (both complete
+    before the loop).  Four passes alternating between two buffers on the full-size configs[1] film: bit-identical to
+    the same passes without the option."""
+    from pbrt_b200 import synth
+
+    res, spp = (1920, 1080), 16
+    filt, *_ = make_filter(gpu, "gaussian")
+    b = (0, 0, *res)
+    bufs = [synth.samples(b, spp, seed=s)[:2] for s in (5, 6)]
+    out = []
+    for on in (False, True):
+        assert gpu.overlap_passes(on) is False
+        f = gpu.Film.new(res, [[0, 0], [1, 1]], filt, 35.0, "x.pfm", 1.0, float("inf"))
+        for i in range(4):
+            f.add_samples_tile([[0, 0], list(res)], spp, *bufs[i & 1], gpu.SPLAT_EXACT)
+        f.check()
+        out.append(f.read_pixels())
+        gpu.overlap_passes(False)
+    assert np.array_equal(u32(out[0]), u32(out[1]))
+
+
 @pytest.mark.parametrize("name", list(oracle.FILTERS))
 def test_c1_matches_committed_golden(gpu, name):
     """CUDA path against the committed fixture alone (no oracle call): device sample generator -> splat -> resolve."""
