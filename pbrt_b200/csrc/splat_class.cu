@@ -1096,7 +1096,12 @@ static int launch_class(const ClassParams &CP0) {
     // render over resident samples); any other launch waits first and overlaps only its table staging.
     static const void *last_xy = nullptr, *last_rgbw = nullptr;
     static uint64_t last_launch = ~0ull;
-    CP.wait_first = !((g_overlap_any || (last_xy == P.xy && last_rgbw == P.rgbw)) && last_launch == ctx().launches && !P.tiles) ||
+    // Overlap pays where segments are short (the tail it fills is a larger share, and the early CTAs' scrambled placement
+    // upsets the rank weights less): +10 % at 14 rows per CTA, +7 % at 28 (C2), +4 % at 60 (a C5 shard of 8), but
+    // -2.4 % at 113 (C3) and -1.2 % at 480 (C5) — so only up to PBRT_B200_PDL_MAX_ROWS (80) rows per CTA.
+    const bool short_segments = P.rows_per_cta <= class_env_int("PBRT_B200_PDL_MAX_ROWS", 80);
+    CP.wait_first = !((g_overlap_any || (last_xy == P.xy && last_rgbw == P.rgbw)) && last_launch == ctx().launches && !P.tiles &&
+                      short_segments) ||
                     class_env_int("PBRT_B200_PDL_WAIT_FIRST", 0);
     last_xy = P.xy;
     last_rgbw = P.rgbw;
