@@ -481,11 +481,9 @@ __global__ void __launch_bounds__(TW, TILES ? 1 : PBRT_CLASS_RESIDENT_THREADS / 
     const int cy1 = TILES ? tb.y1 : CP.seg_start[blockIdx.y + 1];
     const int x = cx0 + tid;
     const bool col_ok = x < tb.x1;
-    const float fx = (float)x;
     const int W = sb.x1 - sb.x0;
     const bool clamp_on = P.max_lum < __int_as_float(0x7f800000);
     const float rH = (float)H;                 // == P.rx == P.ry
-    const float c16 = (1.f / rH) * 16.f;       // inv_radius * 16, exact
 
     // staged nominal pixels of a row: [sx0, sx1); local index = nx - (cx0 - H)
     const int sx0 = max(cx0 - H, sb.x0), sx1 = min(cx0 + TW + H, sb.x1);
