@@ -410,12 +410,16 @@ def main():
     fx.close()
 
     # ---- BASELINE configs[4], the whole render, strong-scaled, one timed region ----------------
-    render = None
+    render = render3 = None
     if not args.no_render_c5 and args.mode != "atomic":
         try:
             render = render_c5(pb, pdist, synth, torch, dist, stream, rank, world, mode, args.render_passes)
         except Exception as e:  # the headline line must still be printed
             render = {"error": f"{type(e).__name__}: {e}"}
+        try:  # BASELINE configs[2] the same way (64 spp = 4 passes)
+            render3 = render_c5(pb, pdist, synth, torch, dist, stream, rank, world, mode, 4, config="c3")
+        except Exception as e:
+            render3 = {"error": f"{type(e).__name__}: {e}"}
 
     # ---- end to end through the public API with host buffers ------------------------------
     e2e = None
@@ -515,7 +519,7 @@ def main():
             "assemble": {"resolve_then_nccl_allgather_ms": assemble_ms, "fused_resolve_peer_store_ms": assemble_fused_ms,
                          "frames_identical": assemble_identical, "bytes_per_rank": max(owned.area(), 0) * 12 * world},
             "percent_of_hbm_peak": 100.0 * achieved / peak,
-            "render_c5": render,
+            "render_c5": render, "render_c3": render3,
         }
         if extras:
             out["extras"] = extras
@@ -529,17 +533,24 @@ def main():
         dist.destroy_process_group()
 
 
-def render_c5(pb, pdist, synth, torch, dist, stream, rank, world, mode, passes=16):
+def render_c5(pb, pdist, synth, torch, dist, stream, rank, world, mode, passes=16, config="c5"):
     """BASELINE configs[4] end to end on the device, STRONG-scaled: the 7680x4320 film row-sharded over `world` GPUs, Lanczos-sinc
     r=4, 256 spp as `passes` pixel-major passes of 16 spp, then the final assembly (fused resolve + NVLink peer stores into
     every rank's full frame) — all inside ONE timed region, device time, max over ranks.  Every pass re-reads the same
     resident 16-spp stream of the shard (12.7 GB at N=1, far above L2): the work per pass is that of a fresh stream, and the
     204 GB of 256 distinct spp would not fit.  At N>1 the block also times one-to-all routing of a pass held by rank 0."""
-    W, H, spp = 7680, 4320, 16
-    filt = pb.LanczosSincFilter((4.0, 4.0), 3.0)
-    film = pb.Film.new([W, H], [[0, 0], [1, 1]], filt, 35.0, "render_c5.pfm", 1.0, float("inf"), rank=rank, nranks=world)
+    # config "c3" = BASELINE configs[2] the same way: 3840x2160, Mitchell r=2, 64 spp as `passes` (4) passes of 16
+    if config == "c3":
+        W, H, spp, radius = 3840, 2160, 16, 2.0
+        filt = pb.MitchellFilter((2.0, 2.0), 1.0 / 3.0, 1.0 / 3.0)
+        label = "3840x2160 film, Mitchell r=2, %d spp as %d pixel-major passes of 16 (BASELINE configs[2])"
+    else:
+        W, H, spp, radius = 7680, 4320, 16, 4.0
+        filt = pb.LanczosSincFilter((4.0, 4.0), 3.0)
+        label = "7680x4320 film, Lanczos-sinc r=4, %d spp as %d pixel-major passes of 16 (BASELINE configs[4])"
+    film = pb.Film.new([W, H], [[0, 0], [1, 1]], filt, 35.0, "render_%s.pfm" % config, 1.0, float("inf"), rank=rank, nranks=world)
     cropped, owned = film.cropped_pixel_bounds, film.owned_pixel_bounds
-    sb = pdist.shard_sample_bounds(cropped, (owned.p_min.y, owned.p_max.y), 4.0)
+    sb = pdist.shard_sample_bounds(cropped, (owned.p_min.y, owned.p_max.y), radius)
     xy_d, rgbw_d, n_local = synth.samples(sb.as4(), spp, seed=1, index_bounds=cropped.as4())
     sbl = [[sb.p_min.x, sb.p_min.y], [sb.p_max.x, sb.p_max.y]]
     fx = pdist.FrameExchange(film)
@@ -569,15 +580,15 @@ def render_c5(pb, pdist, synth, torch, dist, stream, rank, world, mode, passes=1
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms, splat_ms, assemble_ms = (float(v) for v in t)
     n_total = W * H * spp * passes
-    out = {"workload": "7680x4320 film, Lanczos-sinc r=4, %d spp as %d pixel-major passes of 16 (BASELINE configs[4]), rows sharded over %d GPU(s), "
-                       "then fused resolve + peer-store assembly of the full frame on every rank" % (spp * passes, passes, world),
+    out = {"workload": (label % (spp * passes, passes)) + ", rows sharded over %d GPU(s), then fused resolve + peer-store assembly "
+                       "of the full frame on every rank" % world,
            "scaling": "strong", "n_gpus": world, "ms": total_ms, "splat_ms": splat_ms, "assemble_ms": assemble_ms,
            "assemble_share": assemble_ms / total_ms, "samples": n_total, "samples_per_s": n_total / (total_ms * 1e-3),
            "gpu_launches": int(launches), "mode": {pb.SPLAT_EXACT: "exact", pb.SPLAT_FMA: "fma"}.get(mode, str(mode)),
            "samples_per_rank_per_pass_incl_halo": n_local, "timing": "CUDA events on the launching stream, max over ranks",
            "note": "each pass re-reads the same resident 16-spp stream (exceeds L2)"}
     fx.close()
-    if world > 1:
+    if world > 1 and config == "c5":
         # one-to-all routing: rank 0 holds a whole 16-spp pass of a 1920-row band and routes it to the owning shards
         from pbrt_b200.dist import _DeviceArray
         band = pb.Bounds2i.raw(0, 0, W, 1080)
